@@ -1,0 +1,58 @@
+"""Synthetic BOLD voxels for tests and benchmarks.
+
+Own generator (the reference's ``pybold/data.py`` is broken on NumPy >= 1.24 and is out
+of scope): per voxel ``v`` a block paradigm of ``nb_events`` unit boxcars of
+``ceil(avg_dur / t_r)`` samples (ICASSP-2019 setup, examples/icassp_2019/simulation.py:105-111),
+convolved with a normalised SPM HRF of dilation ``delta_v ~ U[0.7, 1.3]`` and Gaussian noise
+scaled to ``snr_db`` with the rule of pybold/data.py:439-444.  Everything is float64 and
+depends only on ``seed0 + v`` so that any voxel range can be regenerated on any rank.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def _hrf_taps(delta, t_r, dur, dt=0.001):
+    """Closed-form SPM taps at the kept samples, non-normalised (pybold/hrf_model.py:12-39)."""
+    n_fine = int(float(dur) / dt)
+    stride = int(t_r / dt)
+    m = np.arange(0, n_fine, stride, dtype=np.float64)
+    s = float(delta) * (m * (float(dur) / (n_fine - 1))) - dt
+    pos = s > 0
+    sp = np.where(pos, s, 1.0)
+    e = np.exp(-sp)
+    h = sp ** 5 * e / math.factorial(5) - 0.167 * sp ** 15 * e / math.factorial(15)
+    return np.where(pos, h, 0.0)
+
+
+def gen_voxels(n_voxels, n_scans, t_r=1.0, hrf_dur=20.0, snr_db=10.0, nb_events=5,
+               avg_dur=12.0, seed0=0, first_voxel=0, delta_range=(0.7, 1.3),
+               return_truth=False):
+    """Return ``y[V, T]`` float64 (and ``z_true[V, T]``, ``delta[V]`` when asked)."""
+    T = int(n_scans)
+    blk = int(math.ceil(avg_dur / t_r))
+    y = np.empty((n_voxels, T))
+    z_all = np.empty((n_voxels, T)) if return_truth else None
+    deltas = np.empty(n_voxels)
+    hi = max(T - blk - 1, 1)
+    for i in range(n_voxels):
+        rng = np.random.RandomState(seed0 + first_voxel + i)
+        onsets = rng.randint(0, hi, nb_events)
+        delta = rng.uniform(*delta_range)
+        z = np.zeros(T)
+        for o in onsets:
+            z[o:o + blk] += 1.0
+        h = _hrf_taps(delta, t_r, hrf_dur)
+        h = h / np.max(np.abs(h))
+        x = np.convolve(h, z)[:T]
+        n = rng.randn(T)
+        n *= np.linalg.norm(x) / (np.linalg.norm(n) + np.finfo(float).eps) / 10.0 ** (snr_db / 20.0)
+        y[i] = x + n
+        deltas[i] = delta
+        if return_truth:
+            z_all[i] = z
+    if return_truth:
+        return y, z_all, deltas
+    return y
