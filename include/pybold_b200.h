@@ -1,0 +1,165 @@
+/*
+ * pybold_b200 -- C ABI of the B200-native batched solver for pyBOLD's hot path.
+ *
+ * The reference (hcherkaoui/pybold) is pure Python and has no FFI layer; its boundary for
+ * this path is the Python signature of `deconv` / `bd` and the duck-typed `op` / `adj`
+ * protocol of `pybold/linear.py`.  Each entry point below names the
+ * reference code (file:line, relative to the reference root) whose per-voxel work it
+ * replaces for a whole batch of voxels.  `pybold_b200/_lib.py` binds them with ctypes;
+ * INTEGRATION.md shows the stub a pyBOLD maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer.  Arrays are row-major `[V, T]` (T fastest),
+ *    `[V, K]` for HRF taps, `[V, n_trace]` for cost traces.
+ *  - `*_stride` arguments are ELEMENT strides between voxels for per-voxel parameters;
+ *    0 means "one value (or one row) shared by every voxel".
+ *  - `_f32` / `_f64` suffix = storage and arithmetic type of the signal arrays.  The HRF
+ *    evaluation, the Lipschitz constant and the theta step always run in double.
+ *  - All functions are asynchronous on `stream` (a `cudaStream_t` passed as `void*`),
+ *    re-entrant, keep no global mutable state and own no memory.
+ *  - Return value: 0 on success, a negative `PB_ERR_*` code, or a positive CUDA error
+ *    code (`cudaError_t`) passed through.  No exceptions cross the boundary.
+ */
+#ifndef PYBOLD_B200_H
+#define PYBOLD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_ERR_INVALID_ARG (-1)  /* null pointer, non-positive size, bad bounds           */
+#define PB_ERR_UNSUPPORTED (-2)  /* T, K, nb_iter or wind above the compiled limits        */
+#define PB_ERR_NO_DEVICE (-3)    /* no sm_100 kernel image can run on the current device   */
+
+typedef void *pb_stream_t;
+
+/* Library identification / limits. */
+int pb_version(void);               /* major*10000 + minor*100 + patch                     */
+int pb_max_T(void);                 /* largest number of scans per voxel                   */
+int pb_max_K(void);                 /* largest number of HRF taps for the solvers          */
+int pb_max_iter(void);              /* largest nb_iter (momentum table lives on chip)      */
+const char *pb_error_string(int code);
+/* Which kernel a solver call with this shape dispatches to: 0 = generic shared-memory
+ * kernel, otherwise R*1000 + KMAX of the register-tiled warp kernel. */
+int pb_solver_variant(int T, int K, int is_f64);
+
+/* ---- A1: DiscretInteg.op / .adj (pybold/linear.py:15-28, :30-43) -------------------- */
+int pb_integ_op_f32(const float *x, float *out, int64_t V, int T, pb_stream_t stream);
+int pb_integ_op_f64(const double *x, double *out, int64_t V, int T, pb_stream_t stream);
+int pb_integ_adj_f32(const float *x, float *out, int64_t V, int T, pb_stream_t stream);
+int pb_integ_adj_f64(const double *x, double *out, int64_t V, int T, pb_stream_t stream);
+
+/* ---- A5: simple_convolve / spectral_convolve and their retro (adjoint) versions ------
+ * out[v,i] = sum_j h[j] x[v,i-j]   (pybold/convolution.py:9-30, :135-164; K.dot, linear.py:91)
+ * out[v,i] = sum_j h[j] x[v,i+j]   (pybold/convolution.py:33-54, :167-196; K.T.dot, linear.py:111) */
+int pb_conv_op_f32(const float *h, int64_t h_stride, const float *x, float *out,
+                   int64_t V, int T, int K, pb_stream_t stream);
+int pb_conv_op_f64(const double *h, int64_t h_stride, const double *x, double *out,
+                   int64_t V, int T, int K, pb_stream_t stream);
+int pb_conv_adj_f32(const float *h, int64_t h_stride, const float *x, float *out,
+                    int64_t V, int T, int K, pb_stream_t stream);
+int pb_conv_adj_f64(const double *h, int64_t h_stride, const double *x, double *out,
+                    int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A2: ConvAndLinear(DiscretInteg(), h).op / .adj (pybold/linear.py:73-113) --------
+ * op: conv(h, cumsum(x));  adj: reversed-cumsum(corr(h, x)). */
+int pb_hrfinteg_op_f32(const float *h, int64_t h_stride, const float *x, float *out,
+                       int64_t V, int T, int K, pb_stream_t stream);
+int pb_hrfinteg_op_f64(const double *h, int64_t h_stride, const double *x, double *out,
+                       int64_t V, int T, int K, pb_stream_t stream);
+int pb_hrfinteg_adj_f32(const float *h, int64_t h_stride, const float *x, float *out,
+                        int64_t V, int T, int K, pb_stream_t stream);
+int pb_hrfinteg_adj_f64(const double *h, int64_t h_stride, const double *x, double *out,
+                        int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A9: spm_hrf (pybold/hrf_model.py:12-39) ------------------------------------------
+ * out_h[v, m] for m < K, K = pb_hrf_len(t_r, dur).  `normalized` != 0 divides by the
+ * maximum over the reference's 1 ms grid (hrf_model.py:33-34).  theta outside [0.5, 2]
+ * is the caller's error to raise (hrf_model.py:17-21); the kernel writes NaN taps. */
+int pb_hrf_len(double t_r, double dur);
+int pb_spm_hrf_f32(const float *theta, double t_r, double dur, int normalized,
+                   float *out_h, int64_t V, int K, pb_stream_t stream);
+int pb_spm_hrf_f64(const double *theta, double t_r, double dur, int normalized,
+                   double *out_h, int64_t V, int K, pb_stream_t stream);
+
+/* ---- A4: spectral_radius_est (pybold/utils.py:94-109) ---------------------------------
+ * Power iteration on A^T A, A = conv(h) o cumsum, from the supplied start x0 (the reference
+ * draws it from the global NumPy RNG).  out_L[v] = ||x_new|| (NOT multiplied by 0.9). */
+int pb_lipschitz_power_f32(const float *h, int64_t h_stride, const float *x0, int64_t x0_stride,
+                           int nb_iter, double tol, float *out_L,
+                           int64_t V, int T, int K, pb_stream_t stream);
+int pb_lipschitz_power_f64(const double *h, int64_t h_stride, const double *x0, int64_t x0_stride,
+                           int nb_iter, double tol, double *out_L,
+                           int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A6 (setup): ||A^T A||_F of _loops_deconv (pybold/bold_signal.py:249-253) -------- */
+int pb_lipschitz_frob_f32(const float *h, int64_t h_stride, float *out_L,
+                          int64_t V, int T, int K, pb_stream_t stream);
+int pb_lipschitz_frob_f64(const double *h, int64_t h_stride, double *out_L,
+                          int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A3: deconv, fixed lambda (pybold/bold_signal.py:49-97) ---------------------------
+ * One persistent kernel: all `nb_iter` iterations of the (aliased) recursion
+ * with the voxel resident on chip.
+ *   L[v*L_stride]       gradient Lipschitz constant actually used (0.9 * power estimate)
+ *   lbda[v*lbda_stride] regularisation
+ *   w0                  optional warm start [V,T] (NULL = zeros, the reference's start)
+ *   out_J [V, nb_iter]  J_k = 0.5||x_k-y||^2 + lbda||w_k||_1, UN-normalised; entries at and
+ *                       after out_niter[v] are left untouched
+ *   out_niter [V]       iterations executed (early stop, Q5)
+ * out_x / out_z / out_dz = x, z, diff_z of the reference's return tuple. */
+int pb_deconv_f32(const float *y, const float *h, int64_t h_stride,
+                  const float *L, int64_t L_stride, const float *lbda, int64_t lbda_stride,
+                  const float *w0, int nb_iter, int early_stopping, int wind, double tol,
+                  float *out_x, float *out_z, float *out_dz, float *out_J, int32_t *out_niter,
+                  int64_t V, int T, int K, pb_stream_t stream);
+int pb_deconv_f64(const double *y, const double *h, int64_t h_stride,
+                  const double *L, int64_t L_stride, const double *lbda, int64_t lbda_stride,
+                  const double *w0, int nb_iter, int early_stopping, int wind, double tol,
+                  double *out_x, double *out_z, double *out_dz, double *out_J, int32_t *out_niter,
+                  int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A7 (+A6, A9, A10): bd, semi-blind deconvolution (pybold/bold_signal.py:281-382) --
+ * One persistent kernel per batch: outer loop of { Frobenius Lipschitz, nb_iter inner
+ * prox-gradient iterations (the outer count is forwarded, Q3), bounded theta step on
+ * 0.5||y - h(theta)*z||^2, cost trace }, then the final inner loop.
+ *   theta0[v*theta0_stride]  start dilation (reference default MAX_DELTA = 2.0)
+ *   z0                       optional warm start [V,T] (NULL = zeros)
+ *   theta_lo / theta_hi      bounds of the theta step (reference default 0.6 / 1.9)
+ *   out_h [V,K] non-normalised taps; out_theta [V];
+ *   out_J / out_r / out_g [V, nb_iter+2] as d['J'], d['r'], d['g']; out_ntrace [V] = number
+ *   of valid trace entries (nb_iter+2 unless the outer early stop fired, Q7). */
+int pb_bd_f32(const float *y, double t_r, double hrf_dur,
+              const float *lbda, int64_t lbda_stride, const float *theta0, int64_t theta0_stride,
+              const float *z0, double theta_lo, double theta_hi,
+              int nb_iter, int early_stopping, int wind, double tol,
+              float *out_x, float *out_z, float *out_dz, float *out_h, float *out_theta,
+              float *out_J, float *out_r, float *out_g, int32_t *out_ntrace,
+              int64_t V, int T, int K, pb_stream_t stream);
+int pb_bd_f64(const double *y, double t_r, double hrf_dur,
+              const double *lbda, int64_t lbda_stride, const double *theta0, int64_t theta0_stride,
+              const double *z0, double theta_lo, double theta_hi,
+              int nb_iter, int early_stopping, int wind, double tol,
+              double *out_x, double *out_z, double *out_dz, double *out_h, double *out_theta,
+              double *out_J, double *out_r, double *out_g, int32_t *out_ntrace,
+              int64_t V, int T, int K, pb_stream_t stream);
+
+/* ---- A10: the theta step alone / hrf_estim (pybold/bold_signal.py:217-239, :329-334) --
+ * theta[v] <- bounded local minimiser of 0.5||y_v - h(theta)*z_v||^2 from theta0;
+ * out_h [V,K] = non-normalised taps at the minimiser; out_cost [V] = the cost there. */
+int pb_hrf_estim_f32(const float *z, const float *y, double t_r, double hrf_dur,
+                     const float *theta0, int64_t theta0_stride, double theta_lo, double theta_hi,
+                     float *out_theta, float *out_h, float *out_cost,
+                     int64_t V, int T, int K, pb_stream_t stream);
+int pb_hrf_estim_f64(const double *z, const double *y, double t_r, double hrf_dur,
+                     const double *theta0, int64_t theta0_stride, double theta_lo, double theta_hi,
+                     double *out_theta, double *out_h, double *out_cost,
+                     int64_t V, int T, int K, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYBOLD_B200_H */

@@ -1,0 +1,69 @@
+"""Array plumbing between NumPy / torch inputs and the device buffers the C ABI works on.
+
+PyTorch is used only to own device memory and streams.  There is deliberately no code
+path here that computes anything on the CPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pybold_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+
+
+def pick_dtype(*arrays, dtype=None):
+    """float32 only when every floating input is float32; the reference is float64 throughout."""
+    if dtype is not None:
+        return {np.float32: torch.float32, np.float64: torch.float64,
+                "float32": torch.float32, "float64": torch.float64}.get(dtype, dtype)
+    seen = []
+    for a in arrays:
+        if isinstance(a, torch.Tensor):
+            seen.append(a.dtype)
+        elif isinstance(a, np.ndarray) and a.dtype.kind == "f":
+            seen.append(torch.float32 if a.dtype == np.float32 else torch.float64)
+    if seen and all(d == torch.float32 for d in seen):
+        return torch.float32
+    return torch.float64
+
+
+def to_device(x, dtype, device=None):
+    """Contiguous CUDA tensor of ``dtype`` (copies host data through pinned memory when large)."""
+    require_cuda()
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    arr = np.ascontiguousarray(np.asarray(x))
+    return torch.from_numpy(arr).to(device=device, dtype=dtype).contiguous()
+
+
+def per_voxel(value, V, dtype, device, name):
+    """Scalar or length-V parameter -> (tensor, element stride) as the C ABI wants it."""
+    if isinstance(value, torch.Tensor):
+        t = value.to(device=device, dtype=dtype).reshape(-1).contiguous()
+    else:
+        t = torch.as_tensor(np.asarray(value, dtype=np.float64).reshape(-1)).to(device=device, dtype=dtype)
+    if t.numel() == 1:
+        return t, 0
+    if t.numel() != V:
+        raise ValueError("%s must be a scalar or have one entry per voxel (%d), got %d"
+                         % (name, V, t.numel()))
+    return t, 1
+
+
+def like_input(t, template):
+    """Return ``t`` as the kind of array the caller passed in (NumPy in -> NumPy out)."""
+    if isinstance(template, torch.Tensor):
+        return t
+    return t.detach().cpu().numpy()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()

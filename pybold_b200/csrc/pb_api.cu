@@ -1,0 +1,339 @@
+// extern "C" boundary of libpybold_b200.so (declared in include/pybold_b200.h).
+// Host-side argument checks, shared-memory sizing, persistent-grid sizing and dispatch between
+// the register-tiled warp kernels (pb_fast.cuh) and the generic kernels (pb_generic.cuh).
+#include <cmath>
+#include <cstdio>
+
+#include "../../include/pybold_b200.h"
+#include "pb_fast_registry.h"
+#include "pb_ops.cuh"
+
+#define PB_VERSION 100   /* 0.1.0 */
+#define PB_MAX_T 4096
+#define PB_MAX_K 64
+#define PB_MAX_ITER 8192
+#define PB_MAX_OP_K 1024
+
+namespace {
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int err = 0;
+};
+
+DeviceInfo device_info() {
+    DeviceInfo d;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        d.err = (int)e;
+        return d;
+    }
+    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return d;
+}
+
+// Pick warps per CTA so that the CTA's dynamic shared memory fits, then a persistent grid of
+// `ctas_per_sm * sm_count` CTAs (or fewer when the batch is small).
+struct LaunchPlan {
+    int warps = 0;
+    int grid = 0;
+    size_t smem = 0;
+};
+
+LaunchPlan plan_launch(const DeviceInfo &d, size_t fixed_bytes, size_t warp_bytes, int64_t V,
+                       int max_warps) {
+    LaunchPlan p;
+    const size_t budget = (size_t)d.max_smem_optin;
+    if (fixed_bytes + warp_bytes > budget) return p;  // warps == 0 => unsupported
+    // aim for two CTAs per SM so that one CTA's tail does not idle the SM
+    size_t per_cta = budget / 2;
+    int w = (int)((per_cta > fixed_bytes ? per_cta - fixed_bytes : 0) / warp_bytes);
+    if (w < 1) w = (int)((budget - fixed_bytes) / warp_bytes);
+    if (w > max_warps) w = max_warps;
+    if (w < 1) w = 1;
+    p.warps = w;
+    p.smem = fixed_bytes + (size_t)w * warp_bytes;
+    const int ctas_per_sm = (int)(budget / p.smem) > 0 ? (int)(budget / p.smem) : 1;
+    int64_t need = (V + w - 1) / w;
+    int64_t cap = (int64_t)d.sm_count * (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+    p.grid = (int)(need < cap ? need : cap);
+    if (p.grid < 1) p.grid = 1;
+    return p;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return (int)e;
+}
+
+int last_error() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
+pb::HrfGrid make_grid(double t_r, double dur, int *n_fine) {
+    pb::HrfGrid g;
+    const int N = (int)(dur / 0.001);        // int(float(dur) / dt), hrf_model.py:25
+    const int stride = (int)(t_r / 0.001);   // int(t_r / dt),       hrf_model.py:36
+    g.t_step = dur / (double)(N - 1);
+    g.stride = stride;
+    g.K = stride > 0 ? (N + stride - 1) / stride : 0;
+    if (n_fine) *n_fine = N;
+    return g;
+}
+
+template <typename real, int OP>
+int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V, int T, int K,
+           pb_stream_t stream) {
+    if (!x || !out || V < 0 || T <= 0) return PB_ERR_INVALID_ARG;
+    if (OP >= pb::OP_CONV && (!h || K <= 0)) return PB_ERR_INVALID_ARG;
+    if (T > PB_MAX_T || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
+    if (V == 0) return PB_OK;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    pb::GenLayout lay = pb::GenLayout::make(T, OP >= pb::OP_CONV ? K : 1, 0, false);
+    LaunchPlan p = plan_launch(d, 0, lay.warp_bytes(sizeof(real)), V, 8);
+    if (!p.warps) return PB_ERR_UNSUPPORTED;
+    auto kern = pb::op_kernel<real, OP>;
+    int e = set_smem(kern, p.smem);
+    if (e) return e;
+    kern<<<p.grid, p.warps * 32, p.smem, (cudaStream_t)stream>>>(h, h_stride, x, out, V, T, K, lay);
+    return last_error();
+}
+
+template <typename real>
+int run_spm_hrf(const real *theta, double t_r, double dur, int normalized, real *out_h, int64_t V,
+                int K, pb_stream_t stream) {
+    if (!theta || !out_h || V < 0 || !(t_r >= 0.001) || !(dur > 0.002)) return PB_ERR_INVALID_ARG;
+    int n_fine = 0;
+    pb::HrfGrid g = make_grid(t_r, dur, &n_fine);
+    if (K != g.K) return PB_ERR_INVALID_ARG;
+    if (V == 0) return PB_OK;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int warps = 4;
+    int64_t need = (V + warps - 1) / warps;
+    int grid = (int)(need < (int64_t)d.sm_count * 8 ? need : (int64_t)d.sm_count * 8);
+    pb::spm_hrf_kernel<real><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(theta, g, n_fine,
+                                                                            normalized, out_h, V);
+    return last_error();
+}
+
+template <typename real>
+int run_lipschitz_power(const real *h, int64_t h_stride, const real *x0, int64_t x0_stride,
+                        int nb_iter, double tol, real *out_L, int64_t V, int T, int K,
+                        pb_stream_t stream) {
+    if (!h || !x0 || !out_L || V < 0 || T <= 0 || K <= 0 || nb_iter < 1) return PB_ERR_INVALID_ARG;
+    if (T > PB_MAX_T || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
+    if (V == 0) return PB_OK;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    pb::GenLayout lay = pb::GenLayout::make(T, K, 0, false);
+    LaunchPlan p = plan_launch(d, 0, lay.warp_bytes(sizeof(real)), V, 8);
+    if (!p.warps) return PB_ERR_UNSUPPORTED;
+    auto kern = pb::lipschitz_power_kernel<real>;
+    int e = set_smem(kern, p.smem);
+    if (e) return e;
+    kern<<<p.grid, p.warps * 32, p.smem, (cudaStream_t)stream>>>(h, h_stride, x0, x0_stride, nb_iter,
+                                                                 tol, out_L, V, T, K, lay);
+    return last_error();
+}
+
+template <typename real>
+int run_lipschitz_frob(const real *h, int64_t h_stride, real *out_L, int64_t V, int T, int K,
+                       pb_stream_t stream) {
+    if (!h || !out_L || V < 0 || T <= 0 || K <= 0) return PB_ERR_INVALID_ARG;
+    if (T > (1 << 20) || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
+    if (V == 0) return PB_OK;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int kp = (K + 3) & ~3;
+    const int warps = 4;
+    const size_t smem = (size_t)warps * 3 * kp * sizeof(double);
+    auto kern = pb::lipschitz_frob_kernel<real>;
+    int e = set_smem(kern, smem);
+    if (e) return e;
+    int64_t need = (V + warps - 1) / warps;
+    int grid = (int)(need < (int64_t)d.sm_count * 8 ? need : (int64_t)d.sm_count * 8);
+    kern<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(h, h_stride, out_L, V, T, K, kp);
+    return last_error();
+}
+
+template <typename real>
+int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
+    if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz || !a.out_J ||
+        !a.out_niter || a.V < 0 || a.T <= 0 || a.K <= 0 || a.nb_iter < 1 || a.wind < 0)
+        return PB_ERR_INVALID_ARG;
+    if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
+    if (a.V == 0) return PB_OK;
+    int rc = pb::fast_deconv_dispatch(a, (cudaStream_t)stream);
+    if (rc != pb::FAST_NO_MATCH) return rc;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const bool es = a.early_stopping && a.wind >= 2;
+    pb::GenLayout lay = pb::GenLayout::make(a.T, a.K, es ? a.wind - 1 : 0, false);
+    const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    LaunchPlan p = plan_launch(d, beta_bytes, lay.warp_bytes(sizeof(real)), a.V, 8);
+    if (!p.warps) return PB_ERR_UNSUPPORTED;
+    auto kern = pb::generic_deconv_kernel<real>;
+    int e = set_smem(kern, p.smem);
+    if (e) return e;
+    kern<<<p.grid, p.warps * 32, p.smem, (cudaStream_t)stream>>>(a, lay);
+    return last_error();
+}
+
+template <typename real>
+int run_bd(pb::BdArgs<real> a, double t_r, double hrf_dur, pb_stream_t stream) {
+    if (!a.y || !a.lbda || !a.theta0 || !a.out_x || !a.out_z || !a.out_dz || !a.out_h ||
+        !a.out_theta || !a.out_J || !a.out_r || !a.out_g || !a.out_ntrace || a.V < 0 || a.T <= 0 ||
+        a.nb_iter < 1 || a.wind < 0 || !(a.theta_lo <= a.theta_hi) || !(t_r >= 0.001) ||
+        !(hrf_dur > 0.002))
+        return PB_ERR_INVALID_ARG;
+    a.grid = make_grid(t_r, hrf_dur, nullptr);
+    if (a.K != a.grid.K) return PB_ERR_INVALID_ARG;
+    if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
+    if (a.V == 0) return PB_OK;
+    int rc = pb::fast_bd_dispatch(a, (cudaStream_t)stream);
+    if (rc != pb::FAST_NO_MATCH) return rc;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    pb::GenLayout lay = pb::GenLayout::make(a.T, a.K, 0, true);
+    const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    LaunchPlan p = plan_launch(d, beta_bytes, lay.warp_bytes(sizeof(real)), a.V, 8);
+    if (!p.warps) return PB_ERR_UNSUPPORTED;
+    auto kern = pb::generic_bd_kernel<real>;
+    int e = set_smem(kern, p.smem);
+    if (e) return e;
+    kern<<<p.grid, p.warps * 32, p.smem, (cudaStream_t)stream>>>(a, lay);
+    return last_error();
+}
+
+template <typename real>
+int run_hrf_estim(const real *z, const real *y, double t_r, double hrf_dur, const real *theta0,
+                  int64_t theta0_stride, double lo, double hi, real *out_theta, real *out_h,
+                  real *out_cost, int64_t V, int T, int K, pb_stream_t stream) {
+    if (!z || !y || !theta0 || !out_theta || !out_h || !out_cost || V < 0 || T <= 0 || !(lo <= hi) ||
+        !(t_r >= 0.001) || !(hrf_dur > 0.002))
+        return PB_ERR_INVALID_ARG;
+    pb::HrfGrid g = make_grid(t_r, hrf_dur, nullptr);
+    if (K != g.K) return PB_ERR_INVALID_ARG;
+    if (T > PB_MAX_T || K > PB_MAX_K) return PB_ERR_UNSUPPORTED;
+    if (V == 0) return PB_OK;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    pb::GenLayout lay = pb::GenLayout::make(T, K, 0, true);
+    LaunchPlan p = plan_launch(d, 0, lay.warp_bytes(sizeof(real)), V, 8);
+    if (!p.warps) return PB_ERR_UNSUPPORTED;
+    auto kern = pb::hrf_estim_kernel<real>;
+    int e = set_smem(kern, p.smem);
+    if (e) return e;
+    kern<<<p.grid, p.warps * 32, p.smem, (cudaStream_t)stream>>>(z, y, g, theta0, theta0_stride, lo, hi,
+                                                                 out_theta, out_h, out_cost, V, T, lay);
+    return last_error();
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb_version(void) { return PB_VERSION; }
+int pb_max_T(void) { return PB_MAX_T; }
+int pb_max_K(void) { return PB_MAX_K; }
+int pb_max_iter(void) { return PB_MAX_ITER; }
+
+const char *pb_error_string(int code) {
+    switch (code) {
+        case PB_OK: return "ok";
+        case PB_ERR_INVALID_ARG: return "invalid argument";
+        case PB_ERR_UNSUPPORTED: return "unsupported shape (T, K, nb_iter or wind above the compiled limits)";
+        case PB_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int pb_solver_variant(int T, int K, int is_f64) { return pb::fast_variant_id(T, K, is_f64 != 0); }
+
+int pb_hrf_len(double t_r, double dur) {
+    if (!(t_r >= 0.001) || !(dur > 0.002)) return PB_ERR_INVALID_ARG;
+    return make_grid(t_r, dur, nullptr).K;
+}
+
+#define PB_DEFINE_OPS(SUF, REAL)                                                                       \
+    int pb_integ_op_##SUF(const REAL *x, REAL *out, int64_t V, int T, pb_stream_t s) {                 \
+        return run_op<REAL, pb::OP_INTEG>(nullptr, 0, x, out, V, T, 0, s);                             \
+    }                                                                                                  \
+    int pb_integ_adj_##SUF(const REAL *x, REAL *out, int64_t V, int T, pb_stream_t s) {                \
+        return run_op<REAL, pb::OP_INTEG_ADJ>(nullptr, 0, x, out, V, T, 0, s);                         \
+    }                                                                                                  \
+    int pb_conv_op_##SUF(const REAL *h, int64_t hs, const REAL *x, REAL *out, int64_t V, int T, int K, \
+                         pb_stream_t s) {                                                              \
+        return run_op<REAL, pb::OP_CONV>(h, hs, x, out, V, T, K, s);                                   \
+    }                                                                                                  \
+    int pb_conv_adj_##SUF(const REAL *h, int64_t hs, const REAL *x, REAL *out, int64_t V, int T,       \
+                          int K, pb_stream_t s) {                                                      \
+        return run_op<REAL, pb::OP_CONV_ADJ>(h, hs, x, out, V, T, K, s);                               \
+    }                                                                                                  \
+    int pb_hrfinteg_op_##SUF(const REAL *h, int64_t hs, const REAL *x, REAL *out, int64_t V, int T,    \
+                             int K, pb_stream_t s) {                                                   \
+        return run_op<REAL, pb::OP_HRFINTEG>(h, hs, x, out, V, T, K, s);                               \
+    }                                                                                                  \
+    int pb_hrfinteg_adj_##SUF(const REAL *h, int64_t hs, const REAL *x, REAL *out, int64_t V, int T,   \
+                              int K, pb_stream_t s) {                                                  \
+        return run_op<REAL, pb::OP_HRFINTEG_ADJ>(h, hs, x, out, V, T, K, s);                           \
+    }                                                                                                  \
+    int pb_spm_hrf_##SUF(const REAL *theta, double t_r, double dur, int normalized, REAL *out_h,       \
+                         int64_t V, int K, pb_stream_t s) {                                            \
+        return run_spm_hrf<REAL>(theta, t_r, dur, normalized, out_h, V, K, s);                         \
+    }                                                                                                  \
+    int pb_lipschitz_power_##SUF(const REAL *h, int64_t hs, const REAL *x0, int64_t xs, int nb_iter,   \
+                                 double tol, REAL *out_L, int64_t V, int T, int K, pb_stream_t s) {    \
+        return run_lipschitz_power<REAL>(h, hs, x0, xs, nb_iter, tol, out_L, V, T, K, s);              \
+    }                                                                                                  \
+    int pb_lipschitz_frob_##SUF(const REAL *h, int64_t hs, REAL *out_L, int64_t V, int T, int K,       \
+                                pb_stream_t s) {                                                       \
+        return run_lipschitz_frob<REAL>(h, hs, out_L, V, T, K, s);                                     \
+    }                                                                                                  \
+    int pb_deconv_##SUF(const REAL *y, const REAL *h, int64_t h_stride, const REAL *L,                 \
+                        int64_t L_stride, const REAL *lbda, int64_t lbda_stride, const REAL *w0,       \
+                        int nb_iter, int early_stopping, int wind, double tol, REAL *out_x,            \
+                        REAL *out_z, REAL *out_dz, REAL *out_J, int32_t *out_niter, int64_t V, int T,  \
+                        int K, pb_stream_t s) {                                                        \
+        pb::DeconvArgs<REAL> a;                                                                        \
+        a.y = y; a.h = h; a.h_stride = h_stride; a.L = L; a.L_stride = L_stride; a.lbda = lbda;        \
+        a.lbda_stride = lbda_stride; a.w0 = w0; a.nb_iter = nb_iter;                                   \
+        a.early_stopping = early_stopping; a.wind = wind; a.tol = tol; a.out_x = out_x;                \
+        a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J; a.out_niter = out_niter; a.V = V;         \
+        a.T = T; a.K = K;                                                                              \
+        return run_deconv<REAL>(a, s);                                                                 \
+    }                                                                                                  \
+    int pb_bd_##SUF(const REAL *y, double t_r, double hrf_dur, const REAL *lbda, int64_t lbda_stride,  \
+                    const REAL *theta0, int64_t theta0_stride, const REAL *z0, double theta_lo,        \
+                    double theta_hi, int nb_iter, int early_stopping, int wind, double tol,            \
+                    REAL *out_x, REAL *out_z, REAL *out_dz, REAL *out_h, REAL *out_theta, REAL *out_J, \
+                    REAL *out_r, REAL *out_g, int32_t *out_ntrace, int64_t V, int T, int K,            \
+                    pb_stream_t s) {                                                                   \
+        pb::BdArgs<REAL> a;                                                                            \
+        a.y = y; a.lbda = lbda; a.lbda_stride = lbda_stride; a.theta0 = theta0;                        \
+        a.theta0_stride = theta0_stride; a.z0 = z0; a.theta_lo = theta_lo; a.theta_hi = theta_hi;      \
+        a.nb_iter = nb_iter; a.early_stopping = early_stopping; a.wind = wind; a.tol = tol;            \
+        a.out_x = out_x; a.out_z = out_z; a.out_dz = out_dz; a.out_h = out_h;                          \
+        a.out_theta = out_theta; a.out_J = out_J; a.out_r = out_r; a.out_g = out_g;                    \
+        a.out_ntrace = out_ntrace; a.V = V; a.T = T; a.K = K;                                          \
+        return run_bd<REAL>(a, t_r, hrf_dur, s);                                                       \
+    }                                                                                                  \
+    int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
+                           const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \
+                           REAL *out_theta, REAL *out_h, REAL *out_cost, int64_t V, int T, int K,      \
+                           pb_stream_t s) {                                                            \
+        return run_hrf_estim<REAL>(z, y, t_r, hrf_dur, theta0, theta0_stride, lo, hi, out_theta,       \
+                                   out_h, out_cost, V, T, K, s);                                       \
+    }
+
+PB_DEFINE_OPS(f32, float)
+PB_DEFINE_OPS(f64, double)
+
+}  // extern "C"

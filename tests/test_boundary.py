@@ -1,0 +1,96 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol the
+header declares, the product never touches the oracle, and the host-side mirror keeps the
+reference's signatures."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "pybold_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pb_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_header_symbols():
+    from pybold_b200 import _lib
+    names = _header_symbols()
+    assert len(names) >= 30
+    for name in names:
+        assert hasattr(_lib.lib, name), "libpybold_b200.so does not export " + name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names
+    assert _lib.lib.pb_version() >= 100
+    assert _lib.lib.pb_max_T() >= 1200 and _lib.lib.pb_max_K() >= 32
+
+
+def test_hrf_len_matches_reference_rule():
+    from pybold_b200 import _lib
+    for t_r, dur, K in [(1.0, 20.0, 20), (0.75, 20.0, 27), (0.72, 20.0, 28), (0.7535, 20.0, 27),
+                        (1.0, 30.0, 30), (2.0, 60.0, 30), (0.1, 10.0, 100)]:
+        assert _lib.lib.pb_hrf_len(t_r, dur) == K
+        assert K == len(range(0, int(dur / 0.001), int(t_r / 0.001)))
+    assert _lib.lib.pb_hrf_len(0.0, 20.0) == _lib.PB_ERR_INVALID_ARG
+
+
+def test_error_strings_and_exceptions():
+    from pybold_b200 import _lib
+    assert _lib.error_string(0) == "ok"
+    assert "invalid" in _lib.error_string(_lib.PB_ERR_INVALID_ARG)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.PB_ERR_INVALID_ARG, "x")
+    with pytest.raises(_lib.PyboldB200Error):
+        _lib.check(700, "x")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pybold_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "pybold_oracle" not in text, f
+
+
+def test_signatures_mirror_the_reference():
+    import pybold_b200 as pb
+    want_bd = ["y", "t_r", "lbda", "theta_0", "z_0", "hrf_dur", "bounds", "nb_iter", "nb_sub_iter",
+               "nb_last_iter", "print_period", "early_stopping", "wind", "tol", "verbose"]
+    got = list(inspect.signature(pb.bd).parameters)
+    assert got[:len(want_bd)] == want_bd
+    sig = inspect.signature(pb.bd).parameters
+    assert sig["lbda"].default == 1.0 and sig["nb_iter"].default == 100 and sig["wind"].default == 4
+    assert sig["tol"].default == 1.0e-12 and sig["early_stopping"].default is False
+    want_dc = ["y", "t_r", "hrf", "lbda", "early_stopping", "tol", "wind", "nb_iter", "nb_sub_iter",
+               "verbose"]
+    got = list(inspect.signature(pb.deconv).parameters)
+    assert got[:len(want_dc)] == want_dc
+    sig = inspect.signature(pb.deconv).parameters
+    assert sig["lbda"].default is None and sig["wind"].default == 6 and sig["nb_iter"].default == 1000
+    want_hrf = ["delta", "t_r", "dur", "normalized_hrf", "dt", "p_delay", "undershoot", "p_disp",
+                "u_disp", "p_u_ratio", "onset"]
+    assert list(inspect.signature(pb.spm_hrf).parameters) == want_hrf
+    assert list(inspect.signature(pb.ConvAndLinear.__init__).parameters)[1:] == \
+        ["M", "kernel", "dim_in", "dim_out", "spectral_conv"]
+    assert pb.MIN_DELTA == 0.5 and pb.MAX_DELTA == 2.0
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    import pybold_b200 as pb
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        pb.bd(np.zeros(16), 1.0)
+
+
+def test_synth_generator_is_rank_independent():
+    from pybold_b200.synth import gen_voxels
+    a = gen_voxels(6, 50, 1.0, 20.0, seed0=3)
+    b = gen_voxels(3, 50, 1.0, 20.0, seed0=3, first_voxel=3)
+    assert np.array_equal(a[3:], b)

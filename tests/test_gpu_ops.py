@@ -1,0 +1,123 @@
+"""GPU parity of the stand-alone operator kernels (through the C ABI) against the golden
+vectors of the live reference and against the CPU oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import pybold_oracle as orc  # noqa: E402
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300)
+
+
+TOL = {np.float64: 1e-13, np.float32: 2e-6}
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_operators_match_reference_golden(golden, dt):
+    import pybold_b200 as pb
+    from pybold_b200 import convolution as cv
+    g = golden("ops")
+    for i in range(int(g["n_cases"])):
+        k, x = g["k%d" % i].astype(dt), g["x%d" % i].astype(dt)
+        T = len(x)
+        tol = TOL[dt] * (10 if dt is np.float32 else 1)
+        assert rel(cv.simple_convolve(k, x), g["conv%d" % i]) < tol
+        assert rel(cv.spectral_convolve(k, x), g["sconv%d" % i]) < tol
+        assert rel(cv.simple_retro_convolve(k, x), g["corr%d" % i]) < tol
+        assert rel(cv.spectral_retro_convolve(k, x), g["scorr%d" % i]) < tol
+        D = pb.DiscretInteg()
+        assert rel(D.op(x), g["integ_op%d" % i]) < tol * 10
+        assert rel(D.adj(x), g["integ_adj%d" % i]) < tol * 10
+        H = pb.ConvAndLinear(pb.DiscretInteg(), k, dim_in=T, dim_out=T)
+        assert rel(H.op(x), g["H_op%d" % i]) < tol * 10
+        assert rel(H.adj(x), g["H_adj%d" % i]) < tol * 10
+        out = cv.simple_convolve(k, x)
+        assert isinstance(out, np.ndarray) and out.dtype == dt and out.shape == x.shape
+
+
+def test_batched_operators_and_dot_test():
+    """<A x, y> == <x, A^T y> on a ragged set of shapes, batched with per-voxel kernels."""
+    import pybold_b200 as pb
+    rng = np.random.RandomState(0)
+    for (V, T, K) in [(1, 1, 1), (3, 7, 9), (65, 300, 20), (17, 1201, 28), (5, 33, 64)]:
+        x = torch.as_tensor(rng.randn(V, T), device="cuda")
+        yv = torch.as_tensor(rng.randn(V, T), device="cuda")
+        k = torch.as_tensor(rng.randn(V, K), device="cuda")
+        H = pb.ConvAndLinear(pb.DiscretInteg(), k, dim_in=T)
+        lhs = torch.sum(H.op(x) * yv, dim=1)
+        rhs = torch.sum(x * H.adj(yv), dim=1)
+        assert torch.allclose(lhs, rhs, rtol=1e-11, atol=1e-9)
+        for v in (0, V - 1):
+            want = orc.conv_causal(k[v].cpu().numpy(), np.cumsum(x[v].cpu().numpy()))
+            assert rel(H.op(x)[v].cpu().numpy(), want) < 1e-12
+
+
+def test_spm_hrf_matches_reference_golden(golden):
+    import pybold_b200 as pb
+    g = golden("spm_hrf")
+    for i, (delta, t_r, dur) in enumerate(g["grid"]):
+        h, t = pb.spm_hrf(delta, t_r, dur, False)
+        hn, _ = pb.spm_hrf(delta, t_r, dur, True)
+        assert h.shape == g["h%d" % i].shape
+        assert rel(h, g["h%d" % i]) < 1e-14
+        assert rel(hn, g["hn%d" % i]) < 1e-14
+        assert np.array_equal(t, g["t%d" % i])
+    # batched thetas on the device
+    th = torch.tensor([0.6, 1.0, 1.9], device="cuda", dtype=torch.float64)
+    hb, _ = pb.spm_hrf(th, 1.0, 20.0, False)
+    assert rel(hb[1].cpu().numpy(), g["h0"]) < 1e-14
+    with pytest.raises(ValueError):
+        pb.spm_hrf(2.5, 1.0, 20.0)
+    with pytest.raises(ValueError):
+        pb.spm_hrf(0.4, 1.0, 20.0)
+
+
+def test_lipschitz_matches_reference_golden(golden):
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    from pybold_b200.utils import spectral_radius_est
+    g = golden("lipschitz")
+    for i, (T, _, _, _) in enumerate(g["cases"]):
+        T = int(T)
+        h = g["h%d" % i]
+        H = pb.ConvAndLinear(pb.DiscretInteg(), h, dim_in=T)
+        got = spectral_radius_est(H, (T,), x0=g["x0_%d" % i])
+        assert abs(got / float(g["power%d" % i]) - 1) < 1e-12
+        # global-RNG behaviour of the reference (utils.py:97)
+        np.random.seed(100 + i)
+        got2 = spectral_radius_est(H, (T,))
+        assert abs(got2 / float(g["power%d" % i]) - 1) < 1e-12
+        hd = torch.as_tensor(h, device="cuda")
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        rc = _lib.lib.pb_lipschitz_frob_f64(hd.data_ptr(), 0, out.data_ptr(), 1, T, len(h), 0)
+        assert rc == 0
+        assert abs(float(out[0]) / float(g["frob%d" % i]) - 1) < 1e-13
+
+
+def test_frobenius_formula_edge_shapes():
+    """Closed-form ||A^T A||_F against the dense Gram matrix, including K > T and K = 1."""
+    from pybold_b200 import _lib
+    rng = np.random.RandomState(5)
+    for (T, K) in [(5, 1), (7, 2), (10, 12), (19, 20), (20, 20), (21, 20), (64, 33), (50, 64), (400, 27)]:
+        h = rng.randn(K)
+        hd = torch.as_tensor(h, device="cuda")
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        assert _lib.lib.pb_lipschitz_frob_f64(hd.data_ptr(), 0, out.data_ptr(), 1, T, K, 0) == 0
+        assert abs(float(out[0]) / orc.frobenius_lipschitz(h, T) - 1) < 1e-12, (T, K)
+
+
+def test_abi_error_codes():
+    from pybold_b200 import _lib
+    x = torch.zeros(8, device="cuda", dtype=torch.float64)
+    assert _lib.lib.pb_integ_op_f64(0, x.data_ptr(), 1, 8, 0) == _lib.PB_ERR_INVALID_ARG
+    assert _lib.lib.pb_integ_op_f64(x.data_ptr(), x.data_ptr(), 1, -3, 0) == _lib.PB_ERR_INVALID_ARG
+    assert _lib.lib.pb_integ_op_f64(x.data_ptr(), x.data_ptr(), 1, 10 ** 6, 0) == _lib.PB_ERR_UNSUPPORTED
+    assert _lib.lib.pb_integ_op_f64(x.data_ptr(), x.data_ptr(), 0, 8, 0) == 0      # empty batch is fine
+    with pytest.raises(ValueError):
+        _lib.check(_lib.PB_ERR_UNSUPPORTED, "x")
