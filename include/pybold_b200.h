@@ -159,6 +159,12 @@ int pb_hrf_estim_f64(const double *z, const double *y, double t_r, double hrf_du
                      double *out_theta, double *out_h, double *out_cost,
                      int64_t V, int T, int K, pb_stream_t stream);
 
+/* ---- measurement utility (not part of the reference API) --------------------------------
+ * FP32 FMA-pipe microbenchmark used as the roofline denominator: launches
+ * `blocks` CTAs of 256 threads, each thread running 8 independent chains of `iters` FFMA.
+ * Executed flops = blocks * 256 * 8 * iters * 2.  `sink` must hold blocks*256 floats. */
+int pb_bench_fma_f32(float *sink, int blocks, int iters, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

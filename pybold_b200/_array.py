@@ -57,7 +57,13 @@ def per_voxel(value, V, dtype, device, name):
 def like_input(t, template):
     """Return ``t`` as the kind of array the caller passed in (NumPy in -> NumPy out)."""
     if isinstance(template, torch.Tensor):
-        return t
+        if template.is_cuda:
+            return t
+        # host tensor in -> host tensor out (pinned when the input was pinned, so that the
+        # device-to-host copy is a plain DMA)
+        out = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=template.is_pinned())
+        out.copy_(t)
+        return out
     return t.detach().cpu().numpy()
 
 

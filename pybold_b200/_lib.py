@@ -64,6 +64,7 @@ _PLAIN = {
     "pb_error_string": ([c_int], c_char_p),
     "pb_solver_variant": ([c_int, c_int, c_int], c_int),
     "pb_hrf_len": ([c_double, c_double], c_int),
+    "pb_bench_fma_f32": ([_P, c_int, c_int, _P], c_int),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_PLAIN) + [n + s for n in _OPS for s in ("_f32", "_f64")])

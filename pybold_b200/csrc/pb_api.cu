@@ -89,6 +89,7 @@ pb::HrfGrid make_grid(double t_r, double dur, int *n_fine) {
 template <typename real, int OP>
 int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V, int T, int K,
            pb_stream_t stream) {
+    if (V == 0) return PB_OK;
     if (!x || !out || V < 0 || T <= 0) return PB_ERR_INVALID_ARG;
     if (OP >= pb::OP_CONV && (!h || K <= 0)) return PB_ERR_INVALID_ARG;
     if (T > PB_MAX_T || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
@@ -108,6 +109,7 @@ int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V,
 template <typename real>
 int run_spm_hrf(const real *theta, double t_r, double dur, int normalized, real *out_h, int64_t V,
                 int K, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
     if (!theta || !out_h || V < 0 || !(t_r >= 0.001) || !(dur > 0.002)) return PB_ERR_INVALID_ARG;
     int n_fine = 0;
     pb::HrfGrid g = make_grid(t_r, dur, &n_fine);
@@ -127,6 +129,7 @@ template <typename real>
 int run_lipschitz_power(const real *h, int64_t h_stride, const real *x0, int64_t x0_stride,
                         int nb_iter, double tol, real *out_L, int64_t V, int T, int K,
                         pb_stream_t stream) {
+    if (V == 0) return PB_OK;
     if (!h || !x0 || !out_L || V < 0 || T <= 0 || K <= 0 || nb_iter < 1) return PB_ERR_INVALID_ARG;
     if (T > PB_MAX_T || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
     if (V == 0) return PB_OK;
@@ -146,6 +149,7 @@ int run_lipschitz_power(const real *h, int64_t h_stride, const real *x0, int64_t
 template <typename real>
 int run_lipschitz_frob(const real *h, int64_t h_stride, real *out_L, int64_t V, int T, int K,
                        pb_stream_t stream) {
+    if (V == 0) return PB_OK;
     if (!h || !out_L || V < 0 || T <= 0 || K <= 0) return PB_ERR_INVALID_ARG;
     if (T > (1 << 20) || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
     if (V == 0) return PB_OK;
@@ -165,6 +169,7 @@ int run_lipschitz_frob(const real *h, int64_t h_stride, real *out_L, int64_t V, 
 
 template <typename real>
 int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
+    if (a.V == 0) return PB_OK;
     if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz || !a.out_J ||
         !a.out_niter || a.V < 0 || a.T <= 0 || a.K <= 0 || a.nb_iter < 1 || a.wind < 0)
         return PB_ERR_INVALID_ARG;
@@ -188,6 +193,7 @@ int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
 
 template <typename real>
 int run_bd(pb::BdArgs<real> a, double t_r, double hrf_dur, pb_stream_t stream) {
+    if (a.V == 0) return PB_OK;
     if (!a.y || !a.lbda || !a.theta0 || !a.out_x || !a.out_z || !a.out_dz || !a.out_h ||
         !a.out_theta || !a.out_J || !a.out_r || !a.out_g || !a.out_ntrace || a.V < 0 || a.T <= 0 ||
         a.nb_iter < 1 || a.wind < 0 || !(a.theta_lo <= a.theta_hi) || !(t_r >= 0.001) ||
@@ -216,6 +222,7 @@ template <typename real>
 int run_hrf_estim(const real *z, const real *y, double t_r, double hrf_dur, const real *theta0,
                   int64_t theta0_stride, double lo, double hi, real *out_theta, real *out_h,
                   real *out_cost, int64_t V, int T, int K, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
     if (!z || !y || !theta0 || !out_theta || !out_h || !out_cost || V < 0 || T <= 0 || !(lo <= hi) ||
         !(t_r >= 0.001) || !(hrf_dur > 0.002))
         return PB_ERR_INVALID_ARG;
@@ -236,9 +243,28 @@ int run_hrf_estim(const real *z, const real *y, double t_r, double hrf_dur, cons
     return last_error();
 }
 
+__global__ void fma_peak_kernel(float *sink, int iters) {
+    float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 }  // namespace
 
 extern "C" {
+
+int pb_bench_fma_f32(float *sink, int blocks, int iters, pb_stream_t stream) {
+    if (!sink || blocks < 1 || iters < 1) return PB_ERR_INVALID_ARG;
+    fma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+    return last_error();
+}
+
 
 int pb_version(void) { return PB_VERSION; }
 int pb_max_T(void) { return PB_MAX_T; }
