@@ -237,8 +237,8 @@ struct WarpVoxel {
 // ------------------------------------------------------------------------------------------------
 // deconv, fixed lambda (pybold/bold_signal.py:49-97)
 // ------------------------------------------------------------------------------------------------
-template <typename real, int R, int KMAX, bool CIRC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename real, int R, int KMAX, bool CIRC, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -343,8 +343,8 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
 // ------------------------------------------------------------------------------------------------
 // bd (pybold/bold_signal.py:281-382)
 // ------------------------------------------------------------------------------------------------
-template <typename real, int R, int KMAX, bool CIRC, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <typename real, int R, int KMAX, bool CIRC, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_bd_kernel(BdArgs<real> p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -523,13 +523,13 @@ int fast_launch(Kern kern, size_t smem, int warps, int64_t V, cudaStream_t strea
     return 0;
 }
 
-template <typename real, int R, int KMAX, bool CIRC, int WARPS>
+template <typename real, int R, int KMAX, bool CIRC, int WARPS, int MINB>
 int fast_deconv_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
     const bool es = a.early_stopping && a.wind >= 2;
     const int ring_rows = es ? a.wind - 1 : 0;
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     const size_t smem = beta_bytes + (size_t)WARPS * ring_rows * R * 32 * sizeof(real);
-    auto kern = fast_deconv_kernel<real, R, KMAX, CIRC, WARPS>;
+    auto kern = fast_deconv_kernel<real, R, KMAX, CIRC, WARPS, MINB>;
     int grid = 0;
     int rc = fast_launch(kern, smem, WARPS, a.V, stream, &grid);
     if (rc == -2) return FAST_NO_MATCH;   // ring does not fit: let the generic kernel decide
@@ -539,11 +539,11 @@ int fast_deconv_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-template <typename real, int R, int KMAX, bool CIRC, int WARPS>
+template <typename real, int R, int KMAX, bool CIRC, int WARPS, int MINB>
 int fast_bd_launch(const BdArgs<real> &a, cudaStream_t stream) {
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     const size_t smem = beta_bytes + (size_t)WARPS * pb_scratch_doubles(KMAX) * sizeof(double);
-    auto kern = fast_bd_kernel<real, R, KMAX, CIRC, WARPS>;
+    auto kern = fast_bd_kernel<real, R, KMAX, CIRC, WARPS, MINB>;
     int grid = 0;
     int rc = fast_launch(kern, smem, WARPS, a.V, stream, &grid);
     if (rc == -2) return FAST_NO_MATCH;
