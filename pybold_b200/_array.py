@@ -59,11 +59,7 @@ def like_input(t, template):
     if isinstance(template, torch.Tensor):
         if template.is_cuda:
             return t
-        # host tensor in -> host tensor out (pinned when the input was pinned, so that the
-        # device-to-host copy is a plain DMA)
-        out = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=template.is_pinned())
-        out.copy_(t)
-        return out
+        return t.cpu()          # host tensor in -> host tensor out
     return t.detach().cpu().numpy()
 
 

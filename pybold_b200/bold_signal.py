@@ -97,16 +97,12 @@ def deconv(y, t_r, hrf, lbda=None, early_stopping=True, tol=1.0e-6,  # noqa
     return (like_input(x, y), like_input(z, y), like_input(dz, y), like_input(Jn, y), None, None)
 
 
-def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stopping, wind, tol):
-    """Device entry point of :func:`bd`: tensors in, dict of tensors out (all ``[V, ...]``)."""
-    V, T = y.shape
-    dtype, dev = y.dtype, y.device
-    K = hrf_len(t_r, hrf_dur)
-    lb, lb_stride = per_voxel(lbda, V, dtype, dev, "lbda")
-    th0, th_stride = per_voxel(theta_0, V, dtype, dev, "theta_0")
-    lo, hi = bounds[0]
-    out = {
-        "x": torch.empty_like(y), "z": torch.empty_like(y), "diff_z": torch.empty_like(y),
+def bd_alloc(V, T, K, nb_iter, dtype, dev):
+    """Output buffers of :func:`bd_batch` (reusable across calls via ``out=``)."""
+    return {
+        "x": torch.empty((V, T), dtype=dtype, device=dev),
+        "z": torch.empty((V, T), dtype=dtype, device=dev),
+        "diff_z": torch.empty((V, T), dtype=dtype, device=dev),
         "h": torch.empty((V, K), dtype=dtype, device=dev),
         "theta": torch.empty(V, dtype=dtype, device=dev),
         "J": torch.full((V, nb_iter + 2), float("nan"), dtype=dtype, device=dev),
@@ -114,6 +110,24 @@ def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stoppin
         "g": torch.full((V, nb_iter + 2), float("nan"), dtype=dtype, device=dev),
         "n_trace": torch.zeros(V, dtype=torch.int32, device=dev),
     }
+
+
+def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stopping, wind, tol,
+             out=None):
+    """Device entry point of :func:`bd`: tensors in, dict of tensors out (all ``[V, ...]``).
+
+    ``out`` (from :func:`bd_alloc`) lets a caller reuse the output buffers; ``lbda`` / ``theta_0``
+    given as device tensors are used in place (no host round trip): the call is then a single
+    asynchronous kernel launch.
+    """
+    V, T = y.shape
+    dtype, dev = y.dtype, y.device
+    K = hrf_len(t_r, hrf_dur)
+    lb, lb_stride = per_voxel(lbda, V, dtype, dev, "lbda")
+    th0, th_stride = per_voxel(theta_0, V, dtype, dev, "theta_0")
+    lo, hi = bounds[0]
+    if out is None:
+        out = bd_alloc(V, T, K, nb_iter, dtype, dev)
     rc = _lib.fn("pb_bd", dtype)(
         ptr(y), float(t_r), float(hrf_dur), ptr(lb), lb_stride, ptr(th0), th_stride, ptr(z_0),
         float(lo), float(hi), int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
