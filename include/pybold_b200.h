@@ -42,8 +42,9 @@ int pb_max_T(void);                 /* largest number of scans per voxel        
 int pb_max_K(void);                 /* largest number of HRF taps for the solvers          */
 int pb_max_iter(void);              /* largest nb_iter (momentum table lives on chip)      */
 const char *pb_error_string(int code);
-/* Which kernel a solver call with this shape dispatches to: 0 = generic shared-memory
- * kernel, otherwise R*1000 + KMAX of the register-tiled warp kernel. */
+/* Which kernel a bd call (no early stopping) with this shape dispatches to: 0 = generic
+ * shared-memory kernel, otherwise G*1000000 + R*1000 + KMAX of the register-tiled kernel
+ * (G lanes per voxel, R samples per lane, KMAX unrolled taps). */
 int pb_solver_variant(int T, int K, int is_f64);
 
 /* ---- A1: DiscretInteg.op / .adj (pybold/linear.py:15-28, :30-43) -------------------- */

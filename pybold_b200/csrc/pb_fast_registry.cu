@@ -15,6 +15,17 @@ struct FastEntry {
 template <typename real>
 const FastEntry<real> *fast_table(int *n);
 
+// group variants (pb_fastg.cuh): several voxels per warp, bd without early stopping only
+template <typename real>
+struct FastGEntry {
+    int R, KMAX, G;
+    bool (*ok)(int T, int K);
+    int (*bd)(const BdArgs<real> &, cudaStream_t);
+};
+
+template <typename real>
+const FastGEntry<real> *fastg_table(int *n);
+
 #include "pb_fast_table.inc"
 
 template <typename real>
@@ -36,6 +47,30 @@ static const FastEntry<real> *pick(int T, int K) {
     return best;
 }
 
+template <typename real>
+static const FastGEntry<real> *pick_group(int T, int K) {
+    int n = 0;
+    const FastGEntry<real> *t = fastg_table<real>(&n);
+    const FastGEntry<real> *best = nullptr;
+    for (int i = 0; i < n; ++i)
+        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G < best->R * best->KMAX * best->G))
+            best = &t[i];
+    return best;
+}
+
+template <typename real>
+static int bd_dispatch(const BdArgs<real> &a, cudaStream_t s) {
+    if (!a.early_stopping) {
+        const FastGEntry<real> *ge = pick_group<real>(a.T, a.K);
+        if (ge) {
+            const int rc = ge->bd(a, s);
+            if (rc != FAST_NO_MATCH) return rc;
+        }
+    }
+    const FastEntry<real> *e = pick<real>(a.T, a.K);
+    return e ? e->bd(a, s) : FAST_NO_MATCH;
+}
+
 int fast_deconv_dispatch(const DeconvArgs<float> &a, cudaStream_t s) {
     const FastEntry<float> *e = pick<float>(a.T, a.K);
     return e ? e->deconv(a, s) : FAST_NO_MATCH;
@@ -44,21 +79,20 @@ int fast_deconv_dispatch(const DeconvArgs<double> &a, cudaStream_t s) {
     const FastEntry<double> *e = pick<double>(a.T, a.K);
     return e ? e->deconv(a, s) : FAST_NO_MATCH;
 }
-int fast_bd_dispatch(const BdArgs<float> &a, cudaStream_t s) {
-    const FastEntry<float> *e = pick<float>(a.T, a.K);
-    return e ? e->bd(a, s) : FAST_NO_MATCH;
-}
-int fast_bd_dispatch(const BdArgs<double> &a, cudaStream_t s) {
-    const FastEntry<double> *e = pick<double>(a.T, a.K);
-    return e ? e->bd(a, s) : FAST_NO_MATCH;
-}
+int fast_bd_dispatch(const BdArgs<float> &a, cudaStream_t s) { return bd_dispatch<float>(a, s); }
+int fast_bd_dispatch(const BdArgs<double> &a, cudaStream_t s) { return bd_dispatch<double>(a, s); }
+
+// id of the kernel a bd call without early stopping uses: G * 1000000 + R * 1000 + KMAX (G = lanes
+// per voxel), 0 = generic kernel
 int fast_variant_id(int T, int K, bool is_f64) {
     if (is_f64) {
+        if (const FastGEntry<double> *g = pick_group<double>(T, K)) return g->G * 1000000 + g->R * 1000 + g->KMAX;
         const FastEntry<double> *e = pick<double>(T, K);
-        return e ? e->R * 1000 + e->KMAX : 0;
+        return e ? 32 * 1000000 + e->R * 1000 + e->KMAX : 0;
     }
+    if (const FastGEntry<float> *g = pick_group<float>(T, K)) return g->G * 1000000 + g->R * 1000 + g->KMAX;
     const FastEntry<float> *e = pick<float>(T, K);
-    return e ? e->R * 1000 + e->KMAX : 0;
+    return e ? 32 * 1000000 + e->R * 1000 + e->KMAX : 0;
 }
 
 }  // namespace pb

@@ -1,0 +1,455 @@
+// Register-tiled persistent bd kernel, GROUP variant: a warp is split into 32/G groups of G lanes,
+// one voxel per group (G = 32, 16 or 8), lane q of a group owns the R contiguous samples
+// [q R, q R + R) of its voxel in registers (G R >= T).
+//
+// Why groups: the per-lane work of an iteration is 2 R K FFMA + ~9 R element-wise ops, while the
+// halo exchange costs 2 (K-1) SHFL and the scans 2 log2(G) SHFL+FADD *per lane whatever R is*.
+// A larger R per lane (fewer lanes per voxel) therefore amortises the non-FFMA instructions:
+// T = 300, K = 20:  G = 32, R = 10  ->  624 issued instructions per voxel-iteration (measured)
+//                   G = 16, R = 19  ->  ~530
+// and no lane idles (16 x 19 = 304 slots for 300 samples instead of 320).
+//
+// Same recursion as pb_fast.cuh (see there); differences:
+//  * shuffles / scans / reductions are segmented (width G);
+//  * only the last TAIL slots of a lane can lie beyond T (dispatcher guarantees G R - T <= TAIL), so
+//    the tail select costs TAIL instead of R instructions;
+//  * tap 0 of the dilated SPM HRF is identically zero (s = -dt < 0, pybold/hrf_model.py:25-30), so
+//    the bd kernel starts its tap loops at j = 1;
+//  * the Lipschitz / theta phases (double, O(K^2)) run group after group with all 32 lanes
+//    cooperating on one voxel's scratch, exactly the code of pb_device.cuh.
+// Early stopping (Q6/Q7) makes groups diverge; those calls are served by pb_fast.cuh (G = 32).
+//
+// Reference code replaced: pybold/bold_signal.py:242-278, :281-382.
+#pragma once
+#include "pb_fast_registry.h"
+#include "pb_generic.cuh"
+
+namespace pb {
+
+// inc <- inc + (value of lane q-d if q >= d), segmented scan step without the ISETP/FSEL pair:
+// shfl.up returns the lane's own value together with a false predicate when the source is out of
+// the segment.
+__device__ __forceinline__ float seg_scan_step_up(float inc, int d, int c) {
+    float out;
+    asm volatile(
+        "{ .reg .f32 r0; .reg .pred p;\n"
+        "  shfl.sync.up.b32 r0|p, %1, %2, %3, 0xffffffff;\n"
+        "  @p add.f32 r0, r0, %1;\n"
+        "  mov.f32 %0, r0; }\n"
+        : "=f"(out) : "f"(inc), "r"(d), "r"(c));
+    return out;
+}
+__device__ __forceinline__ float seg_scan_step_down(float inc, int d, int c) {
+    float out;
+    asm volatile(
+        "{ .reg .f32 r0; .reg .pred p;\n"
+        "  shfl.sync.down.b32 r0|p, %1, %2, %3, 0xffffffff;\n"
+        "  @p add.f32 r0, r0, %1;\n"
+        "  mov.f32 %0, r0; }\n"
+        : "=f"(out) : "f"(inc), "r"(d), "r"(c));
+    return out;
+}
+
+template <typename real, int G>
+struct Seg {
+    static __device__ __forceinline__ real sum(real v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(PB_FULL, v, o, G);
+        return v;
+    }
+    // exclusive prefix over the lanes of the group
+    static __device__ __forceinline__ real excl_up(real v, int q) {
+        real inc = v;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const real t = __shfl_up_sync(PB_FULL, inc, d, G);
+            if (q >= d) inc += t;
+        }
+        const real ex = __shfl_up_sync(PB_FULL, inc, 1, G);
+        return q == 0 ? real(0) : ex;
+    }
+    static __device__ __forceinline__ real excl_down(real v, int q) {
+        real inc = v;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const real t = __shfl_down_sync(PB_FULL, inc, d, G);
+            if (q + d < G) inc += t;
+        }
+        const real ex = __shfl_down_sync(PB_FULL, inc, 1, G);
+        return q == G - 1 ? real(0) : ex;
+    }
+};
+template <int G>
+struct Seg<float, G> {
+    static __device__ __forceinline__ float sum(float v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(PB_FULL, v, o, G);
+        return v;
+    }
+    static __device__ __forceinline__ float excl_up(float v, int q) {
+        float inc = v;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) inc = seg_scan_step_up(inc, d, (32 - G) << 8);
+        const float ex = __shfl_up_sync(PB_FULL, inc, 1, G);
+        return q == 0 ? 0.f : ex;
+    }
+    static __device__ __forceinline__ float excl_down(float v, int q) {
+        float inc = v;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) inc = seg_scan_step_down(inc, d, ((32 - G) << 8) | 0x1f);
+        const float ex = __shfl_down_sync(PB_FULL, inc, 1, G);
+        return q == G - 1 ? 0.f : ex;
+    }
+};
+
+template <typename real, int R, int KMAX, int G, int TAIL, int J0>
+struct GroupVoxel {
+    static_assert(G == 8 || G == 16 || G == 32, "group width");
+    static_assert(TAIL >= 0 && TAIL <= R, "tail");
+    real w[R];     // iterate (the reference's diff_z)
+    real dy[R];    // y[i] - y[i-1]
+    real h[KMAX];  // taps (zero beyond K)
+    int nvalid;    // samples (< T) this lane holds
+    int q;         // lane within the group
+
+    __device__ __forceinline__ void init(int lane, int T) {
+        q = lane & (G - 1);
+        nvalid = max(0, min(R, T - q * R));
+    }
+    // halo[m-1] = a at voxel index (q R - m), zero before the series starts
+    __device__ __forceinline__ void halo_up(const real (&a)[R], real (&halo)[KMAX - 1]) const {
+#pragma unroll
+        for (int m = 1; m < KMAX; ++m) {
+            const int d = (m + R - 1) / R;
+            const int rr = d * R - m;
+            const real t = __shfl_up_sync(PB_FULL, a[rr], d, G);
+            halo[m - 1] = q >= d ? t : real(0);
+        }
+    }
+    // halo[k] = a at voxel index (q R + R + k), zero past the last lane of the group
+    __device__ __forceinline__ void halo_down(const real (&a)[R], real (&halo)[KMAX - 1]) const {
+#pragma unroll
+        for (int k = 0; k < KMAX - 1; ++k) {
+            const int d = (R + k) / R;
+            const int rr = (R + k) - d * R;
+            const real t = __shfl_down_sync(PB_FULL, a[rr], d, G);
+            halo[k] = q + d < G ? t : real(0);
+        }
+    }
+    template <int JS>
+    __device__ __forceinline__ void conv_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
+                                             real (&acc)[R]) const {
+#pragma unroll
+        for (int j = JS; j < KMAX; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int idx = r - j;
+                const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
+                acc[r] = fma(h[j], val, acc[r]);
+            }
+        }
+    }
+    template <int JS>
+    __device__ __forceinline__ void corr_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
+                                             real (&acc)[R]) const {
+#pragma unroll
+        for (int j = JS; j < KMAX; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int idx = r + j;
+                const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
+                acc[r] = fma(h[j], val, acc[r]);
+            }
+        }
+    }
+    __device__ __forceinline__ void scan_fwd(real (&a)[R]) const {
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] += a[r - 1];
+        const real carry = Seg<real, G>::excl_up(a[R - 1], q);
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] += carry;
+    }
+    // zero the slots at and beyond T (only the last TAIL slots of a lane can be)
+    __device__ __forceinline__ void mask_tail(real (&a)[R]) const {
+#pragma unroll
+        for (int r = R - TAIL; r < R; ++r) a[r] = r < nvalid ? a[r] : real(0);
+    }
+    // res <- A w - y
+    __device__ __forceinline__ void forward(real (&res)[R]) const {
+        real halo[KMAX - 1];
+        halo_up(w, halo);
+#pragma unroll
+        for (int r = 0; r < R; ++r) res[r] = -dy[r];
+        conv_acc<J0>(w, halo, res);
+#pragma unroll
+        for (int r = 1; r < R; ++r) res[r] += res[r - 1];
+        const real carry = Seg<real, G>::excl_up(res[R - 1], q);
+#pragma unroll
+        for (int r = 0; r < R; ++r) res[r] += carry;
+        mask_tail(res);
+    }
+    // g <- A^T res
+    __device__ __forceinline__ void adjoint(const real (&res)[R], real (&g)[R]) const {
+        real halo[KMAX - 1];
+        halo_down(res, halo);
+#pragma unroll
+        for (int r = 0; r < R; ++r) g[r] = real(0);
+        corr_acc<J0>(res, halo, g);
+#pragma unroll
+        for (int r = R - 2; r >= 0; --r) g[r] += g[r + 1];
+        const real carry = Seg<real, G>::excl_down(g[0], q);
+#pragma unroll
+        for (int r = 0; r < R; ++r) g[r] += carry;
+    }
+    __device__ __forceinline__ void update(const real (&g)[R], real step, real th, real beta) {
+        const real ob = real(1) + beta;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const real u = fma(-step, g[r], w[r]);
+            const real cl = fmin(fmax(u, -th), th);
+            w[r] = fma(-ob, cl, u);
+        }
+    }
+    __device__ __forceinline__ real partial_sumsq(const real (&a)[R]) const {
+        real s = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s = fma(a[r], a[r], s);
+        return s;
+    }
+    __device__ __forceinline__ real partial_sumabs(const real (&a)[R]) const {
+        real s = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += fabs(a[r]);
+        return s;
+    }
+    __device__ __forceinline__ void load_taps(const double *hs, int K) {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) h[j] = j < K ? (real)hs[j] : real(0);
+    }
+    __device__ __forceinline__ void load_y(const real *yv, int T, real (&y)[R]) const {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q * R + r;
+            y[r] = i < T ? yv[i] : real(0);
+        }
+    }
+    __device__ __forceinline__ void set_dy(const real *yv, int T) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q * R + r;
+            const real cur = i < T ? yv[i] : real(0);
+            const real prv = (i > 0 && i - 1 < T) ? yv[i - 1] : real(0);
+            dy[r] = i < T ? cur - prv : real(0);
+        }
+    }
+    __device__ __forceinline__ void store(real *dst, const real (&a)[R], int T, bool on) const {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q * R + r;
+            if (on && i < T) dst[i] = a[r];
+        }
+    }
+};
+
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fast_bdg_kernel(BdArgs<real> p) {
+    constexpr int VPW = 32 / G;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G;
+    real *beta = reinterpret_cast<real *>(smem);
+    const size_t beta_bytes = ((size_t)p.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    fill_momentum_table(beta, p.nb_iter);
+    ThetaScratch scs[VPW];
+#pragma unroll
+    for (int g = 0; g < VPW; ++g)
+        scs[g].bind(reinterpret_cast<double *>(smem + beta_bytes) +
+                        (size_t)(warp * VPW + g) * pb_scratch_doubles(KMAX), KMAX);
+    ThetaScratch sc = scs[0];
+#pragma unroll
+    for (int g = 1; g < VPW; ++g)
+        if (grp == g) sc = scs[g];
+    const int T = p.T, K = p.K, ntr = p.nb_iter + 2;
+
+    GroupVoxel<real, R, KMAX, G, TAIL, 1> vx;
+    vx.init(lane, T);
+    const int q = vx.q;
+    for (int64_t v0 = ((int64_t)blockIdx.x * WARPS + warp) * VPW; v0 < p.V;
+         v0 += (int64_t)gridDim.x * WARPS * VPW) {
+        const bool on = v0 + grp < p.V;                 // idle groups replay the last voxel
+        const int64_t v = on ? v0 + grp : p.V - 1;
+        const real *yv = p.y + v * T;
+        vx.set_dy(yv, T);
+        const double lam = (double)p.lbda[v * p.lbda_stride];
+        double theta = (double)p.theta0[v * p.theta0_stride];
+#pragma unroll
+        for (int g = 0; g < VPW; ++g) {                   // bold_signal.py:292 (theta_0 itself: Q9)
+            const double th_g = __shfl_sync(PB_FULL, theta, g * G);
+            hrf_eval_warp(th_g, p.grid, scs[g], lane);
+        }
+        vx.load_taps(sc.hs, K);
+        double r0, g0;
+        {
+            real y[R];
+            vx.load_y(yv, T, y);
+            if (p.z0) {                                   // bold_signal.py:298-301
+                const real *zv = p.z0 + v * T;
+                real z[R], hal[KMAX - 1], xr[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int i = q * R + r;
+                    z[r] = i < T ? zv[i] : real(0);
+                    vx.w[r] = (i > 0 && i < T) ? zv[i] - zv[i - 1] : real(0);
+                    xr[r] = -y[r];
+                }
+                vx.halo_up(z, hal);
+                vx.template conv_acc<1>(z, hal, xr);
+                vx.mask_tail(xr);
+                r0 = (double)Seg<real, G>::sum(vx.partial_sumsq(xr));
+                g0 = (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) vx.w[r] = real(0);
+                r0 = (double)Seg<real, G>::sum(vx.partial_sumsq(y));
+                g0 = 0.0;
+            }
+        }
+        const double j0 = r0 + lam * g0;
+        real *Jv = p.out_J + v * (int64_t)ntr, *rv = p.out_r + v * (int64_t)ntr,
+             *gv = p.out_g + v * (int64_t)ntr;
+        const bool writer = on && q == 0;
+        if (writer) {
+            Jv[0] = real(1);
+            rv[0] = real(1);
+            gv[0] = (real)g0;
+        }
+        for (int idx = 0; idx <= p.nb_iter; ++idx) {
+            const bool last = idx == p.nb_iter;           // final deconvolution, :365-376
+            double Lc = 1.0;
+#pragma unroll
+            for (int g = 0; g < VPW; ++g) {
+                const double Lg = frob_lipschitz_warp(scs[g], K, T, lane);
+                if (grp == g) Lc = Lg;
+            }
+            const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
+            for (int j = 0; j < p.nb_iter; ++j) {         // _loops_deconv, :259-276
+                real res[R], gr[R];
+                vx.forward(res);
+                vx.adjoint(res, gr);
+                vx.update(gr, step, th, beta[j]);
+            }
+            real z[R], hal[KMAX - 1], y[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
+            vx.scan_fwd(z);
+            vx.halo_up(z, hal);
+            vx.load_y(yv, T, y);
+            if (!last) {
+                // ---- theta step (:329-334): b = Z^T y, Rz = autocorrelation of z ----
+                real zm[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) zm[r] = z[r];
+                vx.mask_tail(zm);
+#pragma unroll
+                for (int a = 0; a < KMAX; ++a) {
+                    real pb_ = 0, pr = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int id = r - a;
+                        const real zz = id >= 0 ? z[id >= 0 ? id : 0] : hal[id >= 0 ? 0 : -id - 1];
+                        pb_ = fma(y[r], zz, pb_);
+                        pr = fma(zm[r], zz, pr);
+                    }
+                    pb_ = Seg<real, G>::sum(pb_);
+                    pr = Seg<real, G>::sum(pr);
+                    if (q == 0 && a < K) {
+                        sc.b[a] = (double)pb_;
+                        sc.Rz[a] = (double)pr;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int pidx = T - 1 - (q * R + r);
+                    if (pidx >= 0 && pidx < K) sc.zend[pidx] = (double)z[r];
+                }
+                for (int a = q; a < K; a += G)
+                    if (a >= T) sc.zend[a] = 0.0;
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < VPW; ++g) {
+                    gram_build_warp(scs[g], K, lane);
+                    const double th_g = __shfl_sync(PB_FULL, theta, g * G);
+                    const double th_n = theta_solve_warp(th_g, p.theta_lo, p.theta_hi, p.grid, scs[g],
+                                                         lane, nullptr);
+                    hrf_eval_warp(th_n, p.grid, scs[g], lane);
+                    if (grp == g) theta = th_n;
+                }
+                vx.load_taps(sc.hs, K);
+            }
+            // ---- cost trace: x = h * z with the (new) taps ----
+            real xr[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) xr[r] = -y[r];
+            vx.template conv_acc<1>(z, hal, xr);
+            vx.mask_tail(xr);
+            const double rr = (double)Seg<real, G>::sum(vx.partial_sumsq(xr));
+            const double gg = (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            const double eps = last ? 0.0 : 1.0e-30;
+            if (writer) {
+                Jv[idx + 1] = (real)((rr + lam * gg) / j0 + eps);
+                rv[idx + 1] = (real)(rr / r0 + eps);
+                gv[idx + 1] = (real)gg;
+            }
+            if (last) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) xr[r] += y[r];
+                vx.store(p.out_x + v * T, xr, T, on);
+                vx.store(p.out_z + v * T, z, T, on);
+                vx.store(p.out_dz + v * T, vx.w, T, on);
+            }
+            __syncwarp();
+        }
+        if (on)
+            for (int a = q; a < K; a += G) p.out_h[v * K + a] = (real)sc.hs[a];
+        if (writer) {
+            p.out_theta[v] = (real)theta;
+            p.out_ntrace[v] = ntr;
+        }
+        __syncwarp();
+    }
+}
+
+template <int R, int KMAX, int G, int TAIL>
+bool fastg_shape_ok(int T, int K) {
+    return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;
+}
+
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
+    constexpr int VPW = 32 / G;
+    const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    const size_t smem = beta_bytes + (size_t)WARPS * VPW * pb_scratch_doubles(KMAX) * sizeof(double);
+    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB>;
+    int dev = 0, sms = 0, max_smem = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_smem) return FAST_NO_MATCH;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return FAST_NO_MATCH;
+    const int64_t per_cta = (int64_t)WARPS * VPW;
+    const int64_t need = (a.V + per_cta - 1) / per_cta;
+    const int64_t cap = (int64_t)sms * occ;
+    const int grid = (int)(need < cap ? need : cap);
+    kern<<<grid, WARPS * 32, smem, stream>>>(a);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace pb

@@ -169,3 +169,32 @@ def test_hrf_estim_vs_exact_minimiser(golden):
     assert abs(J[-1] / orc.hrf_fit_err_fast(th, z, y, 1.0, 20.0) - 1) < 1e-9
     for t, val in zip(g["thetas"][::4], g["vals"][::4]):
         assert abs(pb.hrf_fit_err(t, z, y, 1.0, 20.0) / val - 1) < 1e-12
+
+
+@pytest.mark.parametrize("T,t_r", [(296, 1.0), (299, 1.0), (304, 1.0), (233, 0.75), (305, 1.0), (64, 1.0)])
+def test_bd_kernel_variants_tail_shapes(T, t_r):
+    """Shapes at the edges of the register-tiled variants (group kernel tail, linear kernel,
+    short series), odd batch so that one group of the last warp idles."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    V = 3
+    y = gen_voxels(V, T, t_r, 20.0, seed0=5000 + T)
+    x, z, dz, h, d = pb.bd(y, t_r, lbda=1.2, theta_0=2.0, hrf_dur=20.0, nb_iter=15)
+    assert _lib.lib.pb_solver_variant(T, h.shape[1], 1) != 0
+    for v in range(V):
+        xo, zo, wo, ho, do = orc.bd(y[v], t_r, lbda=1.2, theta_0=2.0, hrf_dur=20.0, nb_iter=15,
+                                    theta_solver="exact")
+        assert rel(z[v], zo) < 1e-8 and rel(x[v], xo) < 1e-8 and rel(dz[v], wo) < 1e-8, (T, v)
+        assert rel(h[v], ho) < 1e-8 and rel(d["J"][v], do["J"]) < 1e-9, (T, v)
+
+
+def test_bd_generic_kernel_matches_fast_kernel():
+    """K = 40 taps (t_r = 0.5 s) has no register-tiled instantiation: generic kernel."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    T, t_r = 200, 0.5
+    y = gen_voxels(2, T, t_r, 20.0, seed0=6000)
+    x, z, dz, h, d = pb.bd(y, t_r, lbda=1.0, nb_iter=12)
+    assert h.shape[1] == 40 and _lib.lib.pb_solver_variant(T, 40, 1) == 0
+    xo, zo, wo, ho, do = orc.bd(y[1], t_r, lbda=1.0, nb_iter=12, theta_solver="exact")
+    assert rel(z[1], zo) < 1e-8 and rel(h[1], ho) < 1e-8 and rel(d["J"][1], do["J"]) < 1e-9

@@ -1,0 +1,112 @@
+// Developer experiment (not shipped): times fast_bdg_kernel instantiations and checks them against
+// fast_bd_kernel (G = 32) on the same random data.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "pb_fast.cuh"
+#include "pb_fastg.cuh"
+
+using namespace pb;
+
+static HrfGrid make_grid(double t_r, double dur) {
+    HrfGrid g; const int N = (int)(dur / 0.001); const int stride = (int)(t_r / 0.001);
+    g.t_step = dur / (double)(N - 1); g.stride = stride; g.K = (N + stride - 1) / stride; return g;
+}
+
+struct Bufs {
+    BdArgs<float> a; std::vector<float> z, theta; int64_t V; int T;
+    float *dy, *lb, *th, *x, *dz_, *zz, *h, *theta_d, *J, *r, *g; int32_t *nt;
+    void alloc(int64_t V_, int T_, double t_r, int nb_iter) {
+        V = V_; T = T_;
+        a.grid = make_grid(t_r, 20.0); a.K = a.grid.K; a.T = T; a.V = V;
+        std::vector<float> y((size_t)V * T);
+        srand(1);
+        // block-like signal + noise so that the theta step has something to fit
+        for (int64_t v = 0; v < V; ++v) {
+            int on = rand() % (T - 40);
+            for (int i = 0; i < T; ++i) {
+                float s = (i > on + 4 && i < on + 30) ? 1.0f : 0.0f;
+                y[v * T + i] = s + 0.3f * ((float)rand() / RAND_MAX - 0.5f);
+            }
+        }
+        cudaMalloc(&dy, V * T * 4); cudaMemcpy(dy, y.data(), V * T * 4, cudaMemcpyHostToDevice);
+        float one = 1.7f, two = 2.0f;
+        cudaMalloc(&lb, 4); cudaMemcpy(lb, &one, 4, cudaMemcpyHostToDevice);
+        cudaMalloc(&th, 4); cudaMemcpy(th, &two, 4, cudaMemcpyHostToDevice);
+        cudaMalloc(&x, V * T * 4); cudaMalloc(&zz, V * T * 4); cudaMalloc(&dz_, V * T * 4);
+        cudaMalloc(&h, V * a.K * 4); cudaMalloc(&theta_d, V * 4);
+        cudaMalloc(&J, V * (nb_iter + 2) * 4); cudaMalloc(&r, V * (nb_iter + 2) * 4); cudaMalloc(&g, V * (nb_iter + 2) * 4);
+        cudaMalloc(&nt, V * 4);
+        a.y = dy; a.lbda = lb; a.lbda_stride = 0; a.theta0 = th; a.theta0_stride = 0; a.z0 = nullptr;
+        a.theta_lo = 0.6; a.theta_hi = 1.9; a.nb_iter = nb_iter; a.early_stopping = 0; a.wind = 4; a.tol = 1e-12;
+        a.out_x = x; a.out_z = zz; a.out_dz = dz_; a.out_h = h; a.out_theta = theta_d; a.out_J = J; a.out_r = r; a.out_g = g;
+        a.out_ntrace = nt;
+    }
+    void fetch() {
+        z.resize((size_t)V * T); theta.resize(V);
+        cudaMemcpy(z.data(), zz, V * T * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(theta.data(), theta_d, V * 4, cudaMemcpyDeviceToHost);
+    }
+    void free_all() { cudaFree(dy); cudaFree(x); cudaFree(zz); cudaFree(dz_); cudaFree(h); cudaFree(theta_d); cudaFree(J); cudaFree(r); cudaFree(g); cudaFree(nt); }
+};
+
+static std::vector<float> ref_z, ref_theta;
+
+template <typename F, typename Kern>
+void time_it(const char *name, Bufs &b, F launch, Kern kern, int warps, size_t smem, int nb_iter, bool is_ref) {
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    cudaMemset(b.zz, 0, b.V * b.T * 4);
+    int rc = launch(); cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0); rc = launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    b.fetch();
+    double dz = 0, dt = 0, nz = 0;
+    if (is_ref) { ref_z = b.z; ref_theta = b.theta; }
+    for (size_t i = 0; i < b.z.size(); ++i) { dz = fmax(dz, fabs(b.z[i] - ref_z[i])); nz = fmax(nz, fabs(ref_z[i])); }
+    for (size_t i = 0; i < b.theta.size(); ++i) dt = fmax(dt, fabs(b.theta[i] - ref_theta[i]));
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
+    const int K = b.a.K, T = b.T; const double MAC = (double)T * K - K * (K - 1) / 2.0;
+    const double flops = (double)b.V * ((double)(nb_iter + 1) * nb_iter * (4 * MAC + 11 * T));
+    printf("%-30s rc=%d regs=%3d spill=%4zu occ=%d (%2d warps) T=%d K=%d: %8.2f ms %9.0f vox/s %6.2f Tflop/s | z err %.2e (max %.2f) theta err %.2e\n",
+           name, rc, fa.numRegs, (size_t)fa.localSizeBytes, occ, occ * warps, T, K, best, b.V / best * 1e3, flops / best / 1e9, dz, nz, dt);
+}
+
+template <int R, int KMAX, bool CIRC, int WARPS, int MINB>
+void run32(const char *name, Bufs &b, int nb_iter, bool is_ref) {
+    auto kern = fast_bd_kernel<float, R, KMAX, CIRC, WARPS, MINB>;
+    const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * pb_scratch_doubles(KMAX) * 8;
+    time_it(name, b, [&] { return fast_bd_launch<float, R, KMAX, CIRC, WARPS, MINB>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
+}
+template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+void rung(const char *name, Bufs &b, int nb_iter) {
+    auto kern = fast_bdg_kernel<float, R, KMAX, G, TAIL, WARPS, MINB>;
+    const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * (32 / G) * pb_scratch_doubles(KMAX) * 8;
+    time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB>(b.a, 0); }, kern, WARPS, smem, nb_iter, false);
+}
+
+int main(int argc, char **argv) {
+    const int set = argc > 1 ? atoi(argv[1]) : 0;
+    if (set == 0) {
+        Bufs b; b.alloc(40000, 300, 1.0, 100);
+        run32<10, 20, true, 4, 5>("G32 R10 K20 circ W4 M5 (ref)", b, 100, true);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100);
+        rung<19, 20, 16, 8, 4, 4>("G16 R19 K20 T8 W4 M4", b, 100);
+        rung<19, 20, 16, 8, 4, 5>("G16 R19 K20 T8 W4 M5", b, 100);
+        rung<38, 20, 8, 8, 4, 2>("G8  R38 K20 T8 W4 M2", b, 100);
+        rung<38, 20, 8, 8, 4, 3>("G8  R38 K20 T8 W4 M3", b, 100);
+        rung<10, 20, 32, 10, 4, 5>("G32 R10 K20 T10 W4 M5", b, 100);
+        b.free_all();
+    } else {
+        Bufs b; b.alloc(8000, 1200, 0.72, 100);
+        run32<40, 28, true, 8, 1>("G32 R40 K28 circ W8 M1 (ref)", b, 100, true);
+        rung<38, 28, 32, 16, 4, 2>("G32 R38 K28 T16 W4 M2", b, 100);
+        rung<38, 28, 32, 16, 8, 1>("G32 R38 K28 T16 W8 M1", b, 100);
+        b.free_all();
+    }
+    return 0;
+}
