@@ -28,6 +28,7 @@ import numpy as np
 from scipy.optimize import fmin_l_bfgs_b
 from scipy.stats import gamma as _gamma
 
+THETA_XTOL = 1.0e-12   # step tolerance of the exact theta solver (same constant on the device)
 MIN_DELTA = 0.5   # pybold/hrf_model.py:8
 MAX_DELTA = 2.0   # pybold/hrf_model.py:9
 
@@ -411,7 +412,7 @@ def bracketed_newton(gc, theta, lo, hi, max_iter=100):
         if x_new == x:
             return x
         x = x_new
-        if abs(dx) <= 4.0e-16 * max(1.0, abs(x)):
+        if abs(dx) <= THETA_XTOL * max(1.0, abs(x)):
             return x
         gx, cx = gc(x)
         if gx == 0.0:

@@ -13,6 +13,11 @@
 #include <stdint.h>
 
 #define PB_FULL 0xffffffffu
+// Newton on f'(theta) stops when the step falls below this (relative to max(1, |theta|)).  The
+// evaluation noise of f' (double rounding of M h - b) puts a floor of ~1e-14 on the step, so a
+// tighter tolerance would only burn the iteration cap; the reference's own L-BFGS-B answer is
+// ~1e-8 away from the minimiser.
+#define PB_THETA_XTOL 1.0e-12
 
 namespace pb {
 
@@ -326,7 +331,7 @@ __device__ __forceinline__ double theta_solve_warp(double theta_prev, double lo,
                 if (x_new == x) break;
                 x = x_new;
                 result = x;
-                if (fabs(dx) <= 4.0e-16 * fmax(1.0, fabs(x))) break;
+                if (fabs(dx) <= PB_THETA_XTOL * fmax(1.0, fabs(x))) break;
                 theta_eval_warp(x, grid, sc, lane, gx, cx);
                 ++evals;
                 if (gx == 0.0) break;

@@ -1,4 +1,6 @@
 // Dispatch over the register-tiled instantiations listed in pb_fast_table.inc.
+#include <cstdlib>
+
 #include "pb_fast_registry.h"
 
 namespace pb {
@@ -60,7 +62,9 @@ static const FastGEntry<real> *pick_group(int T, int K) {
 
 template <typename real>
 static int bd_dispatch(const BdArgs<real> &a, cudaStream_t s) {
-    if (!a.early_stopping) {
+    // PB_DISABLE_GROUP=1: developer switch for A/B timing of the two register-tiled kernels
+    static const bool no_group = getenv("PB_DISABLE_GROUP") != nullptr;
+    if (!a.early_stopping && !no_group) {
         const FastGEntry<real> *ge = pick_group<real>(a.T, a.K);
         if (ge) {
             const int rc = ge->bd(a, s);

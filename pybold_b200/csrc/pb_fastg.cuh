@@ -15,14 +15,15 @@
 //    the tail select costs TAIL instead of R instructions;
 //  * tap 0 of the dilated SPM HRF is identically zero (s = -dt < 0, pybold/hrf_model.py:25-30), so
 //    the bd kernel starts its tap loops at j = 1;
-//  * the Lipschitz / theta phases (double, O(K^2)) run group after group with all 32 lanes
-//    cooperating on one voxel's scratch, exactly the code of pb_device.cuh.
+//  * the Lipschitz / theta phases (double, O(K^2)) run for all groups of the warp in lock step
+//    (pb_theta_group.cuh): measured, running them group after group cost 14 % of the kernel.
 // Early stopping (Q6/Q7) makes groups diverge; those calls are served by pb_fast.cuh (G = 32).
 //
 // Reference code replaced: pybold/bold_signal.py:242-278, :281-382.
 #pragma once
 #include "pb_fast_registry.h"
 #include "pb_generic.cuh"
+#include "pb_theta_group.cuh"
 
 namespace pb {
 
@@ -102,15 +103,22 @@ struct Seg<float, G> {
     }
 };
 
-template <typename real, int R, int KMAX, int G, int TAIL, int J0>
+// LEAN = true keeps only the iterate in registers: dy lives in shared memory ([r][lane], one
+// conflict-free LDS per sample and iteration) and the taps are fetched four at a time (LDS.128,
+// broadcast within the group) right before their R FFMA each.  ~40 registers less per thread, i.e.
+// more resident warps to hide the scan / shuffle latencies, for ~3 % more instructions.
+template <typename real, int R, int KMAX, int G, int TAIL, int J0, bool LEAN = false>
 struct GroupVoxel {
     static_assert(G == 8 || G == 16 || G == 32, "group width");
     static_assert(TAIL >= 0 && TAIL <= R, "tail");
-    real w[R];     // iterate (the reference's diff_z)
-    real dy[R];    // y[i] - y[i-1]
-    real h[KMAX];  // taps (zero beyond K)
-    int nvalid;    // samples (< T) this lane holds
-    int q;         // lane within the group
+    static_assert(!LEAN || KMAX % 4 == 0, "LEAN fetches taps as 16-byte vectors");
+    real w[R];                     // iterate (the reference's diff_z)
+    real dy[LEAN ? 1 : R];         // y[i] - y[i-1]            (registers unless LEAN)
+    real h[LEAN ? 1 : KMAX];       // taps, zero beyond K       (registers unless LEAN)
+    real *dy_s;                    // LEAN: dy[r] at dy_s[r * 32]  (pointer already offset by lane)
+    const real *h_s;               // LEAN: this group's KMAX taps, 16-byte aligned
+    int nvalid;                    // samples (< T) this lane holds
+    int q;                         // lane within the group
 
     __device__ __forceinline__ void init(int lane, int T) {
         q = lane & (G - 1);
@@ -136,29 +144,66 @@ struct GroupVoxel {
             halo[k] = q + d < G ? t : real(0);
         }
     }
+    struct alignas(4 * sizeof(real)) Tap4 { real t[4]; };
     template <int JS>
     __device__ __forceinline__ void conv_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
+        if constexpr (LEAN) {
 #pragma unroll
-        for (int j = JS; j < KMAX; ++j) {
+            for (int jj = 0; jj < KMAX / 4; ++jj) {
+                const Tap4 t4 = reinterpret_cast<const Tap4 *>(h_s)[jj];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r - j;
-                const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
-                acc[r] = fma(h[j], val, acc[r]);
+                for (int jx = 0; jx < 4; ++jx) {
+                    const int j = 4 * jj + jx;
+                    if (j < JS) continue;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int idx = r - j;
+                        const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
+                        acc[r] = fma(t4.t[jx], val, acc[r]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = JS; j < KMAX; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int idx = r - j;
+                    const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
+                    acc[r] = fma(h[j], val, acc[r]);
+                }
             }
         }
     }
     template <int JS>
     __device__ __forceinline__ void corr_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
+        if constexpr (LEAN) {
 #pragma unroll
-        for (int j = JS; j < KMAX; ++j) {
+            for (int jj = 0; jj < KMAX / 4; ++jj) {
+                const Tap4 t4 = reinterpret_cast<const Tap4 *>(h_s)[jj];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r + j;
-                const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
-                acc[r] = fma(h[j], val, acc[r]);
+                for (int jx = 0; jx < 4; ++jx) {
+                    const int j = 4 * jj + jx;
+                    if (j < JS) continue;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int idx = r + j;
+                        const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
+                        acc[r] = fma(t4.t[jx], val, acc[r]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = JS; j < KMAX; ++j) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int idx = r + j;
+                    const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
+                    acc[r] = fma(h[j], val, acc[r]);
+                }
             }
         }
     }
@@ -179,7 +224,7 @@ struct GroupVoxel {
         real halo[KMAX - 1];
         halo_up(w, halo);
 #pragma unroll
-        for (int r = 0; r < R; ++r) res[r] = -dy[r];
+        for (int r = 0; r < R; ++r) res[r] = LEAN ? -dy_s[r * 32] : -dy[LEAN ? 0 : r];
         conv_acc<J0>(w, halo, res);
 #pragma unroll
         for (int r = 1; r < R; ++r) res[r] += res[r - 1];
@@ -222,9 +267,16 @@ struct GroupVoxel {
         for (int r = 0; r < R; ++r) s += fabs(a[r]);
         return s;
     }
+    // taps of this group's voxel from the double scratch (call with the whole warp converged)
     __device__ __forceinline__ void load_taps(const double *hs, int K) {
+        if constexpr (LEAN) {
+            __syncwarp();
+            for (int j = q; j < KMAX; j += G) const_cast<real *>(h_s)[j] = j < K ? (real)hs[j] : real(0);
+            __syncwarp();
+        } else {
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) h[j] = j < K ? (real)hs[j] : real(0);
+            for (int j = 0; j < KMAX; ++j) h[LEAN ? 0 : j] = j < K ? (real)hs[j] : real(0);
+        }
     }
     __device__ __forceinline__ void load_y(const real *yv, int T, real (&y)[R]) const {
 #pragma unroll
@@ -239,7 +291,8 @@ struct GroupVoxel {
             const int i = q * R + r;
             const real cur = i < T ? yv[i] : real(0);
             const real prv = (i > 0 && i - 1 < T) ? yv[i - 1] : real(0);
-            dy[r] = i < T ? cur - prv : real(0);
+            const real d = i < T ? cur - prv : real(0);
+            if (LEAN) dy_s[r * 32] = d; else dy[LEAN ? 0 : r] = d;
         }
     }
     __device__ __forceinline__ void store(real *dst, const real (&a)[R], int T, bool on) const {
@@ -251,7 +304,13 @@ struct GroupVoxel {
     }
 };
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+template <typename real, int R, int KMAX, int G, bool LEAN>
+__host__ __device__ constexpr size_t fastg_warp_bytes() {
+    return (size_t)(32 / G) * pb_scratch_doubles(KMAX) * sizeof(double) +
+           (LEAN ? ((size_t)R * 32 + (size_t)(32 / G) * KMAX) * sizeof(real) : 0);
+}
+
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_bdg_kernel(BdArgs<real> p) {
     constexpr int VPW = 32 / G;
@@ -261,19 +320,24 @@ fast_bdg_kernel(BdArgs<real> p) {
     real *beta = reinterpret_cast<real *>(smem);
     const size_t beta_bytes = ((size_t)p.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     fill_momentum_table(beta, p.nb_iter);
+    unsigned char *wbase = smem + beta_bytes + (size_t)warp * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
     ThetaScratch scs[VPW];
 #pragma unroll
     for (int g = 0; g < VPW; ++g)
-        scs[g].bind(reinterpret_cast<double *>(smem + beta_bytes) +
-                        (size_t)(warp * VPW + g) * pb_scratch_doubles(KMAX), KMAX);
+        scs[g].bind(reinterpret_cast<double *>(wbase) + (size_t)g * pb_scratch_doubles(KMAX), KMAX);
     ThetaScratch sc = scs[0];
 #pragma unroll
     for (int g = 1; g < VPW; ++g)
         if (grp == g) sc = scs[g];
     const int T = p.T, K = p.K, ntr = p.nb_iter + 2;
 
-    GroupVoxel<real, R, KMAX, G, TAIL, 1> vx;
+    GroupVoxel<real, R, KMAX, G, TAIL, 1, LEAN> vx;
     vx.init(lane, T);
+    if (LEAN) {
+        real *lean = reinterpret_cast<real *>(wbase + (size_t)VPW * pb_scratch_doubles(KMAX) * sizeof(double));
+        vx.h_s = lean + grp * KMAX;
+        vx.dy_s = lean + VPW * KMAX + lane;
+    }
     const int q = vx.q;
     for (int64_t v0 = ((int64_t)blockIdx.x * WARPS + warp) * VPW; v0 < p.V;
          v0 += (int64_t)gridDim.x * WARPS * VPW) {
@@ -283,11 +347,7 @@ fast_bdg_kernel(BdArgs<real> p) {
         vx.set_dy(yv, T);
         const double lam = (double)p.lbda[v * p.lbda_stride];
         double theta = (double)p.theta0[v * p.theta0_stride];
-#pragma unroll
-        for (int g = 0; g < VPW; ++g) {                   // bold_signal.py:292 (theta_0 itself: Q9)
-            const double th_g = __shfl_sync(PB_FULL, theta, g * G);
-            hrf_eval_warp(th_g, p.grid, scs[g], lane);
-        }
+        hrf_eval_group<G>(theta, p.grid, sc, q);           // bold_signal.py:292 (theta_0 itself: Q9)
         vx.load_taps(sc.hs, K);
         double r0, g0;
         {
@@ -319,6 +379,9 @@ fast_bdg_kernel(BdArgs<real> p) {
         real *Jv = p.out_J + v * (int64_t)ntr, *rv = p.out_r + v * (int64_t)ntr,
              *gv = p.out_g + v * (int64_t)ntr;
         const bool writer = on && q == 0;
+#ifdef PB_DEBUG_EVALS
+        int dbg_evals = 0;
+#endif
         if (writer) {
             Jv[0] = real(1);
             rv[0] = real(1);
@@ -326,12 +389,7 @@ fast_bdg_kernel(BdArgs<real> p) {
         }
         for (int idx = 0; idx <= p.nb_iter; ++idx) {
             const bool last = idx == p.nb_iter;           // final deconvolution, :365-376
-            double Lc = 1.0;
-#pragma unroll
-            for (int g = 0; g < VPW; ++g) {
-                const double Lg = frob_lipschitz_warp(scs[g], K, T, lane);
-                if (grp == g) Lc = Lg;
-            }
+            const double Lc = frob_lipschitz_group<G>(sc, K, T, q);
             const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
             for (int j = 0; j < p.nb_iter; ++j) {         // _loops_deconv, :259-276
                 real res[R], gr[R];
@@ -376,15 +434,15 @@ fast_bdg_kernel(BdArgs<real> p) {
                 for (int a = q; a < K; a += G)
                     if (a >= T) sc.zend[a] = 0.0;
                 __syncwarp();
-#pragma unroll
-                for (int g = 0; g < VPW; ++g) {
-                    gram_build_warp(scs[g], K, lane);
-                    const double th_g = __shfl_sync(PB_FULL, theta, g * G);
-                    const double th_n = theta_solve_warp(th_g, p.theta_lo, p.theta_hi, p.grid, scs[g],
-                                                         lane, nullptr);
-                    hrf_eval_warp(th_n, p.grid, scs[g], lane);
-                    if (grp == g) theta = th_n;
-                }
+                gram_build_group<G>(sc, K, q);
+#ifdef PB_DEBUG_EVALS
+                int ne = 0;
+                theta = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, &ne);
+                dbg_evals += ne;
+#else
+                theta = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, nullptr);
+#endif
+                hrf_eval_group<G>(theta, p.grid, sc, q);
                 vx.load_taps(sc.hs, K);
             }
             // ---- cost trace: x = h * z with the (new) taps ----
@@ -414,7 +472,11 @@ fast_bdg_kernel(BdArgs<real> p) {
             for (int a = q; a < K; a += G) p.out_h[v * K + a] = (real)sc.hs[a];
         if (writer) {
             p.out_theta[v] = (real)theta;
+#ifdef PB_DEBUG_EVALS
+            p.out_ntrace[v] = dbg_evals;
+#else
             p.out_ntrace[v] = ntr;
+#endif
         }
         __syncwarp();
     }
@@ -425,12 +487,12 @@ bool fastg_shape_ok(int T, int K) {
     return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
 int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
     constexpr int VPW = 32 / G;
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
-    const size_t smem = beta_bytes + (size_t)WARPS * VPW * pb_scratch_doubles(KMAX) * sizeof(double);
-    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB>;
+    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
+    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN>;
     int dev = 0, sms = 0, max_smem = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
