@@ -46,6 +46,10 @@ const char *pb_error_string(int code);
  * shared-memory kernel, otherwise G*1000000 + R*1000 + KMAX of the register-tiled kernel
  * (G lanes per voxel, R samples per lane, KMAX unrolled taps). */
 int pb_solver_variant(int T, int K, int is_f64);
+/* Voxels that one full wave of the persistent bd grid holds on the current device (0 when the
+ * shape runs on a kernel without that notion).  Hosts that stream a large batch in chunks should
+ * cut it at multiples of this number. */
+int pb_bd_wave_voxels(int T, int K, int is_f64, int nb_iter);
 
 /* ---- A1: DiscretInteg.op / .adj (pybold/linear.py:15-28, :30-43) -------------------- */
 int pb_integ_op_f32(const float *x, float *out, int64_t V, int T, pb_stream_t stream);

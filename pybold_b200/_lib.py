@@ -64,6 +64,7 @@ _PLAIN = {
     "pb_error_string": ([c_int], c_char_p),
     "pb_solver_variant": ([c_int, c_int, c_int], c_int),
     "pb_hrf_len": ([c_double, c_double], c_int),
+    "pb_bd_wave_voxels": ([c_int, c_int, c_int, c_int], c_int),
     "pb_bench_fma_f32": ([_P, c_int, c_int, _P], c_int),
 }
 

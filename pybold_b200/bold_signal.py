@@ -137,6 +137,114 @@ def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stoppin
     return out
 
 
+# ---- host-resident batches: chunked, double-buffered streaming ------------------------------
+_STREAM_MIN_VOXELS = 8192      # below this a single launch is used
+_STREAM_TARGET_CHUNK = 32768   # approximate chunk size, rounded to whole waves of the grid
+_staging_cache = {}
+
+
+def _staging(key, shapes, dtype):
+    """Pinned staging buffers, cached across calls (cudaHostAlloc is expensive)."""
+    bufs = _staging_cache.get(key)
+    if bufs is None:
+        if len(_staging_cache) > 8:
+            _staging_cache.clear()
+        bufs = {k: torch.empty(shp, dtype=(torch.int32 if k == "n_trace" else dtype), pin_memory=True)
+                for k, shp in shapes.items()}
+        _staging_cache[key] = bufs
+    return bufs
+
+
+def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stopping, wind,
+                 tol):
+    """``bd`` for a HOST ``[V, T]`` batch: the batch is cut into chunks of whole grid waves; while
+    the kernel solves chunk i, chunk i+1 is uploaded and chunk i-1 is downloaded (two CUDA streams,
+    pinned staging), so that the host<->device copies hide behind the solve.  Returns CPU tensors.
+    """
+    V, T = yh.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    K = hrf_len(t_r, hrf_dur)
+    ntr = nb_iter + 2
+    wave = _lib.lib.pb_bd_wave_voxels(T, K, int(dtype == torch.float64), int(nb_iter))
+    chunk = _STREAM_TARGET_CHUNK
+    if wave > 0:
+        chunk = max(wave, (chunk // wave) * wave)
+    chunk = min(chunk, V)
+    shapes = {"x": (chunk, T), "z": (chunk, T), "diff_z": (chunk, T), "h": (chunk, K),
+              "theta": (chunk,), "J": (chunk, ntr), "r": (chunk, ntr), "g": (chunk, ntr),
+              "n_trace": (chunk,)}
+    final = {k: torch.empty((V,) + shp[1:], dtype=(torch.int32 if k == "n_trace" else dtype))
+             for k, shp in shapes.items()}
+
+    def host_vec(val):
+        if isinstance(val, torch.Tensor):
+            val = val.detach().cpu().numpy()
+        return np.asarray(val, dtype=np.float64).reshape(-1)
+
+    lb_all, th_all = host_vec(lbda), host_vec(theta_0)
+    z0h = None
+    if z_0 is not None:
+        z0h = (z_0 if isinstance(z_0, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(z_0)))
+        z0h = z0h.reshape(V, T)
+    slots = []
+    for s_idx in range(2):
+        slots.append({
+            "stream": torch.cuda.Stream(device=dev),
+            "event": torch.cuda.Event(),
+            "y": torch.empty((chunk, T), dtype=dtype, device=dev),
+            "z0": torch.empty((chunk, T), dtype=dtype, device=dev) if z0h is not None else None,
+            "out": bd_alloc(chunk, T, K, nb_iter, dtype, dev),
+            "stage_in": _staging(("in", s_idx, chunk, T, dtype), {"y": (chunk, T), "z0": (chunk, T)}, dtype),
+            "stage_out": _staging(("out", s_idx, chunk, T, K, ntr, dtype), shapes, dtype),
+            "range": None,
+        })
+
+    def drain(slot):
+        if slot["range"] is None:
+            return
+        lo, hi = slot["range"]
+        slot["event"].synchronize()
+        for k in final:
+            final[k][lo:hi].copy_(slot["stage_out"][k][:hi - lo])
+        slot["range"] = None
+
+    main = torch.cuda.current_stream()
+    n_chunks = (V + chunk - 1) // chunk
+    for i in range(n_chunks):
+        lo, hi = i * chunk, min((i + 1) * chunk, V)
+        n = hi - lo
+        slot = slots[i % 2]
+        drain(slot)
+        src = yh[lo:hi]
+        if not (src.is_pinned() and src.dtype == dtype):
+            slot["stage_in"]["y"][:n].copy_(src)
+            src = slot["stage_in"]["y"][:n]
+        z0src = None
+        if z0h is not None:
+            slot["stage_in"]["z0"][:n].copy_(z0h[lo:hi])
+            z0src = slot["stage_in"]["z0"][:n]
+        st = slot["stream"]
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            slot["y"][:n].copy_(src, non_blocking=True)
+            if z0src is not None:
+                slot["z0"][:n].copy_(z0src, non_blocking=True)
+            lb = lb_all if lb_all.size == 1 else lb_all[lo:hi]
+            th = th_all if th_all.size == 1 else th_all[lo:hi]
+            out = {k: v[:n] for k, v in slot["out"].items()}
+            bd_batch(slot["y"][:n], t_r, lb, th, slot["z0"][:n] if z0src is not None else None,
+                     hrf_dur, bounds, nb_iter, early_stopping, wind, tol, out=out)
+            for k in final:
+                slot["stage_out"][k][:n].copy_(out[k], non_blocking=True)
+            slot["event"].record(st)
+        slot["range"] = (lo, hi)
+    for slot in slots:
+        drain(slot)
+    main.wait_stream(slots[0]["stream"])
+    main.wait_stream(slots[1]["stream"])
+    return final
+
+
 def bd(y, t_r, lbda=1.0, theta_0=None, z_0=None, hrf_dur=20.0,  # noqa
        bounds=None, nb_iter=100, nb_sub_iter=1000, nb_last_iter=10000,
        print_period=50, early_stopping=False, wind=4, tol=1.0e-12, verbose=0, dtype=None):
@@ -148,7 +256,6 @@ def bd(y, t_r, lbda=1.0, theta_0=None, z_0=None, hrf_dur=20.0,  # noqa
     count and ``nb_sub_iter`` / ``nb_last_iter`` are accepted and ignored (bold_signal.py:324,366).
     """
     dtype = pick_dtype(y, dtype=dtype)
-    yb, one_d = _as_batch(y, dtype)
     theta_0 = MAX_DELTA if theta_0 is None else theta_0                    # bold_signal.py:291
     th_chk = np.asarray(theta_0.detach().cpu() if isinstance(theta_0, torch.Tensor) else theta_0,
                         dtype=np.float64)
@@ -157,6 +264,18 @@ def bd(y, t_r, lbda=1.0, theta_0=None, z_0=None, hrf_dur=20.0,  # noqa
             MIN_DELTA, MAX_DELTA, th_chk))
     if bounds is None:
         bounds = [(MIN_DELTA + 1.0e-1, MAX_DELTA - 1.0e-1)]                # bold_signal.py:303-304
+    host_in = not (isinstance(y, torch.Tensor) and y.is_cuda)
+    if host_in and np.ndim(y) == 2 and len(y) >= _STREAM_MIN_VOXELS:
+        from ._array import require_cuda
+        require_cuda()
+        yh = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+        out = _bd_streamed(yh.contiguous(), dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter,
+                           early_stopping, wind, tol)
+        conv = (lambda t: t) if isinstance(y, torch.Tensor) else (lambda t: t.numpy())
+        d = {k: conv(out[k]) for k in ("J", "r", "g", "theta", "n_trace")}
+        d["l_alpha"] = []
+        return conv(out["x"]), conv(out["z"]), conv(out["diff_z"]), conv(out["h"]), d
+    yb, one_d = _as_batch(y, dtype)
     z0 = None
     if z_0 is not None:
         z0 = to_device(z_0, dtype).reshape(yb.shape)

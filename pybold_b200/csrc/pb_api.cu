@@ -283,6 +283,11 @@ const char *pb_error_string(int code) {
 
 int pb_solver_variant(int T, int K, int is_f64) { return pb::fast_variant_id(T, K, is_f64 != 0); }
 
+int pb_bd_wave_voxels(int T, int K, int is_f64, int nb_iter) {
+    if (T <= 0 || K <= 0 || nb_iter < 1) return 0;
+    return pb::fast_bd_wave_voxels(T, K, is_f64 != 0, nb_iter);
+}
+
 int pb_hrf_len(double t_r, double dur) {
     if (!(t_r >= 0.001) || !(dur > 0.002)) return PB_ERR_INVALID_ARG;
     return make_grid(t_r, dur, nullptr).K;

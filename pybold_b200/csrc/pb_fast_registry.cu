@@ -23,6 +23,7 @@ struct FastGEntry {
     int R, KMAX, G;
     bool (*ok)(int T, int K);
     int (*bd)(const BdArgs<real> &, cudaStream_t);
+    int (*wave)(int nb_iter);
 };
 
 template <typename real>
@@ -85,6 +86,15 @@ int fast_deconv_dispatch(const DeconvArgs<double> &a, cudaStream_t s) {
 }
 int fast_bd_dispatch(const BdArgs<float> &a, cudaStream_t s) { return bd_dispatch<float>(a, s); }
 int fast_bd_dispatch(const BdArgs<double> &a, cudaStream_t s) { return bd_dispatch<double>(a, s); }
+
+int fast_bd_wave_voxels(int T, int K, bool is_f64, int nb_iter) {
+    if (is_f64) {
+        const FastGEntry<double> *g = pick_group<double>(T, K);
+        return g ? g->wave(nb_iter) : 0;
+    }
+    const FastGEntry<float> *g = pick_group<float>(T, K);
+    return g ? g->wave(nb_iter) : 0;
+}
 
 // id of the kernel a bd call without early stopping uses: G * 1000000 + R * 1000 + KMAX (G = lanes
 // per voxel), 0 = generic kernel

@@ -16,5 +16,8 @@ int fast_bd_dispatch(const BdArgs<float> &a, cudaStream_t stream);
 int fast_bd_dispatch(const BdArgs<double> &a, cudaStream_t stream);
 // 0 = generic kernel, else R * 1000 + KMAX
 int fast_variant_id(int T, int K, bool is_f64);
+// voxels per full wave of the persistent bd grid (0 when unknown): batch sizes that are multiples
+// of it waste no tail
+int fast_bd_wave_voxels(int T, int K, bool is_f64, int nb_iter);
 
 }  // namespace pb

@@ -482,6 +482,31 @@ fast_bdg_kernel(BdArgs<real> p) {
     }
 }
 
+// voxels one full wave of the persistent grid holds (SMs x resident CTAs x voxels per CTA)
+template <typename Kern>
+int fast_wave_voxels(Kern kern, int threads, size_t smem, int voxels_per_cta) {
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return sms * occ * voxels_per_cta;
+}
+
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
+int fast_bdg_wave(int nb_iter) {
+    const size_t beta_bytes = ((size_t)nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
+    return fast_wave_voxels(fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN>, WARPS * 32, smem,
+                            WARPS * (32 / G));
+}
+
 template <int R, int KMAX, int G, int TAIL>
 bool fastg_shape_ok(int T, int K) {
     return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;

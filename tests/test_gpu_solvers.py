@@ -198,3 +198,31 @@ def test_bd_generic_kernel_matches_fast_kernel():
     assert h.shape[1] == 40 and _lib.lib.pb_solver_variant(T, 40, 1) == 0
     xo, zo, wo, ho, do = orc.bd(y[1], t_r, lbda=1.0, nb_iter=12, theta_solver="exact")
     assert rel(z[1], zo) < 1e-8 and rel(h[1], ho) < 1e-8 and rel(d["J"][1], do["J"]) < 1e-9
+
+
+def test_bd_streamed_host_batch_equals_single_launch():
+    """Host batches above the streaming threshold are solved chunk by chunk with overlapped copies;
+    the result must be bit-identical to the single-launch path, including per-voxel parameters
+    and a warm start."""
+    import pybold_b200 as pb
+    from pybold_b200 import bold_signal as bs
+    V, T = 9001, 48
+    rng = np.random.RandomState(1)
+    y = gen_voxels(64, T, 1.0, 20.0, seed0=7000)
+    y = np.tile(y, (V // 64 + 1, 1))[:V] * rng.uniform(0.5, 1.5, (V, 1))
+    lb = rng.uniform(0.5, 2.0, V)
+    z0 = np.zeros((V, T))
+    z0[:, 10:20] = 1.0
+    old = bs._STREAM_TARGET_CHUNK
+    bs._STREAM_TARGET_CHUNK = 4096      # force 3 chunks
+    try:
+        a = pb.bd(y.astype(np.float32), 1.0, lbda=lb, z_0=z0, nb_iter=6)
+    finally:
+        bs._STREAM_TARGET_CHUNK = old
+    yt = torch.as_tensor(y.astype(np.float32), device="cuda")
+    b = pb.bd(yt, 1.0, lbda=lb, z_0=z0, nb_iter=6)
+    assert isinstance(a[0], np.ndarray) and a[0].shape == (V, T)
+    for u, v in zip(a[:4], b[:4]):
+        assert np.array_equal(u, v.cpu().numpy())
+    for k in ("J", "r", "g", "theta", "n_trace"):
+        assert np.array_equal(a[4][k], b[4][k].cpu().numpy()), k

@@ -81,7 +81,7 @@ void time_it(const char *name, Bufs &b, F launch, Kern kern, int warps, size_t s
       printf("    theta evals per voxel: mean %.1f max %d (per outer iteration %.2f)\n", s / b.V, mx, s / b.V / nb_iter); }
 #endif
     double dz = 0, dt = 0, nz = 0;
-    if (is_ref) { ref_z = b.z; ref_theta = b.theta; }
+    if (is_ref || ref_z.size() != b.z.size()) { ref_z = b.z; ref_theta = b.theta; }
     for (size_t i = 0; i < b.z.size(); ++i) { dz = fmax(dz, fabs(b.z[i] - ref_z[i])); nz = fmax(nz, fabs(ref_z[i])); }
     for (size_t i = 0; i < b.theta.size(); ++i) dt = fmax(dt, fabs(b.theta[i] - ref_theta[i]));
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
@@ -98,24 +98,32 @@ void run32(const char *name, Bufs &b, int nb_iter, bool is_ref) {
     time_it(name, b, [&] { return fast_bd_launch<float, R, KMAX, CIRC, WARPS, MINB>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
 template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
-void rung(const char *name, Bufs &b, int nb_iter) {
+void rung(const char *name, Bufs &b, int nb_iter, bool is_ref = false) {
     auto kern = fast_bdg_kernel<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>;
     const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * fastg_warp_bytes<float, R, KMAX, G, LEAN>();
-    time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>(b.a, 0); }, kern, WARPS, smem, nb_iter, false);
+    time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
 
 int main(int argc, char **argv) {
     const int set = argc > 1 ? atoi(argv[1]) : 0;
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
-        run32<10, 20, true, 4, 5>("G32 R10 K20 circ W4 M5 (ref)", b, 100, true);
-        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
+        rung<19, 20, 16, 8, 5, 3>("G16 R19 K20 T8 W5 M3", b, 100);
+        rung<19, 20, 16, 8, 8, 2>("G16 R19 K20 T8 W8 M2", b, 100);
+        rung<19, 20, 16, 8, 4, 4, true>("G16 R19 K20 T8 W4 M4 LEAN", b, 100);
+        rung<19, 20, 16, 8, 5, 3, true>("G16 R19 K20 T8 W5 M3 LEAN", b, 100);
+        rung<19, 20, 16, 8, 4, 3, true>("G16 R19 K20 T8 W4 M3 LEAN", b, 100);
+        rung<19, 20, 16, 4, 4, 3>("G16 R19 K20 T4 W4 M3", b, 100);
+        rung<10, 20, 32, 10, 4, 5>("G32 R10 K20 T10 W4 M5", b, 100);
         b.free_all();
     } else {
         Bufs b; b.alloc(8000, 1200, 0.72, 100);
         run32<40, 28, true, 8, 1>("G32 R40 K28 circ W8 M1 (ref)", b, 100, true);
-        rung<38, 28, 32, 16, 4, 2>("G32 R38 K28 T16 W4 M2", b, 100);
         rung<38, 28, 32, 16, 8, 1>("G32 R38 K28 T16 W8 M1", b, 100);
+        rung<38, 28, 32, 16, 8, 1, true>("G32 R38 K28 T16 W8 M1 LEAN", b, 100);
+        rung<38, 28, 32, 16, 6, 2, true>("G32 R38 K28 T16 W6 M2 LEAN", b, 100);
+        
         b.free_all();
     }
     return 0;
