@@ -28,6 +28,9 @@ struct FastGEntry {
 
 template <typename real>
 const FastGEntry<real> *fastg_table(int *n);
+// CTA variants (pb_fastc.cuh): NW warps per voxel; same entry type, G = 32 * NW
+template <typename real>
+const FastGEntry<real> *fastc_table(int *n);
 
 #include "pb_fast_table.inc"
 
@@ -53,8 +56,13 @@ static const FastEntry<real> *pick(int T, int K) {
 template <typename real>
 static const FastGEntry<real> *pick_group(int T, int K) {
     int n = 0;
-    const FastGEntry<real> *t = fastg_table<real>(&n);
+    const FastGEntry<real> *t = fastc_table<real>(&n);
     const FastGEntry<real> *best = nullptr;
+    for (int i = 0; i < n; ++i)
+        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G < best->R * best->KMAX * best->G))
+            best = &t[i];
+    if (best) return best;
+    t = fastg_table<real>(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G < best->R * best->KMAX * best->G))
             best = &t[i];

@@ -6,6 +6,7 @@
 #include <vector>
 #include "pb_fast.cuh"
 #include "pb_fastg.cuh"
+#include "pb_fastc.cuh"
 
 using namespace pb;
 
@@ -104,6 +105,13 @@ void rung(const char *name, Bufs &b, int nb_iter, bool is_ref = false) {
     time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
 
+template <int R, int KMAX, int NW, int MINB>
+void runc(const char *name, Bufs &b, int nb_iter) {
+    auto kern = fast_bdc_kernel<float, R, KMAX, NW, MINB>;
+    const size_t smem = CtaLayout<float, R, KMAX, NW>::bytes(nb_iter);
+    time_it(name, b, [&] { return fast_bdc_launch<float, R, KMAX, NW, MINB>(b.a, 0); }, kern, NW, smem, nb_iter, false);
+}
+
 int main(int argc, char **argv) {
     const int set = argc > 1 ? atoi(argv[1]) : 0;
     if (set == 0) {
@@ -117,13 +125,20 @@ int main(int argc, char **argv) {
         rung<19, 20, 16, 4, 4, 3>("G16 R19 K20 T4 W4 M3", b, 100);
         rung<10, 20, 32, 10, 4, 5>("G32 R10 K20 T10 W4 M5", b, 100);
         b.free_all();
+    } else if (set == 2) {
+        Bufs b; b.alloc(16000, 600, 1.0, 100);
+        run32<20, 20, true, 4, 3>("G32 R20 K20 circ W4 M3 (ref)", b, 100, true);
+        runc<20, 20, 1, 8>("CTA R20 K20 NW1 M8", b, 100);
+        runc<20, 20, 1, 12>("CTA R20 K20 NW1 M12", b, 100);
+        runc<20, 20, 1, 16>("CTA R20 K20 NW1 M16", b, 100);
+        b.free_all();
     } else {
         Bufs b; b.alloc(8000, 1200, 0.72, 100);
         run32<40, 28, true, 8, 1>("G32 R40 K28 circ W8 M1 (ref)", b, 100, true);
-        rung<38, 28, 32, 16, 8, 1>("G32 R38 K28 T16 W8 M1", b, 100);
-        rung<38, 28, 32, 16, 8, 1, true>("G32 R38 K28 T16 W8 M1 LEAN", b, 100);
-        rung<38, 28, 32, 16, 6, 2, true>("G32 R38 K28 T16 W6 M2 LEAN", b, 100);
-        
+        runc<20, 28, 2, 6>("CTA R20 K28 NW2 M6", b, 100);
+        runc<20, 28, 2, 7>("CTA R20 K28 NW2 M7", b, 100);
+        runc<20, 28, 2, 8>("CTA R20 K28 NW2 M8", b, 100);
+        runc<12, 28, 4, 4>("CTA R12 K28 NW4 M4", b, 100);
         b.free_all();
     }
     return 0;
