@@ -107,8 +107,17 @@ struct Seg<float, G> {
 // conflict-free LDS per sample and iteration) and the taps are fetched four at a time (LDS.128,
 // broadcast within the group) right before their R FFMA each.  ~40 registers less per thread, i.e.
 // more resident warps to hide the scan / shuffle latencies, for ~3 % more instructions.
-template <typename real, int R, int KMAX, int G, int TAIL, int J0, bool LEAN = false>
+// SMH = true exchanges the K-1 halo samples through shared memory instead of shuffles: every lane
+// stores its R values as 16-byte vectors into a per-voxel buffer framed by zero pads and loads the
+// preceding / following samples as vectors (R % 4 == 0).  10 + 10 instead of 38 + 38 instructions
+// per convolution pair at K = 20 and no boundary selects; measured +17 % at T = 600 (pb_fastc.cuh).
+template <typename real, int R, int KMAX, int G, int TAIL, int J0, bool LEAN = false, bool SMH = false>
 struct GroupVoxel {
+    static_assert(!SMH || R % 4 == 0, "SMH moves 16-byte vectors");
+    static constexpr int NH = (KMAX - 1 + 3) / 4;   // vectors per halo
+    struct alignas(4 * sizeof(real)) V4 { real t[4]; };
+    real *myA;                     // SMH: this lane's R slots in the iterate buffer
+    real *myB;                     // SMH: this lane's R slots in the residual buffer
     static_assert(G == 8 || G == 16 || G == 32, "group width");
     static_assert(TAIL >= 0 && TAIL <= R, "tail");
     static_assert(!LEAN || KMAX % 4 == 0, "LEAN fetches taps as 16-byte vectors");
@@ -124,8 +133,29 @@ struct GroupVoxel {
         q = lane & (G - 1);
         nvalid = max(0, min(R, T - q * R));
     }
+    __device__ __forceinline__ void put(real *dst, const real (&a)[R]) const {
+#pragma unroll
+        for (int r4 = 0; r4 < R / 4; ++r4) {
+            V4 t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t.t[e] = a[4 * r4 + e];
+            reinterpret_cast<V4 *>(dst)[r4] = t;
+        }
+    }
     // halo[m-1] = a at voxel index (q R - m), zero before the series starts
     __device__ __forceinline__ void halo_up(const real (&a)[R], real (&halo)[KMAX - 1]) const {
+        if constexpr (SMH) {
+            put(myA, a);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+                const V4 t = reinterpret_cast<const V4 *>(myA)[-1 - c];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * c + (3 - e) < KMAX - 1) halo[4 * c + (3 - e) < KMAX - 1 ? 4 * c + (3 - e) : 0] = t.t[e];
+            }
+            return;
+        }
 #pragma unroll
         for (int m = 1; m < KMAX; ++m) {
             const int d = (m + R - 1) / R;
@@ -136,6 +166,18 @@ struct GroupVoxel {
     }
     // halo[k] = a at voxel index (q R + R + k), zero past the last lane of the group
     __device__ __forceinline__ void halo_down(const real (&a)[R], real (&halo)[KMAX - 1]) const {
+        if constexpr (SMH) {
+            put(myB, a);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+                const V4 t = reinterpret_cast<const V4 *>(myB + R)[c];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * c + e < KMAX - 1) halo[4 * c + e < KMAX - 1 ? 4 * c + e : 0] = t.t[e];
+            }
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < KMAX - 1; ++k) {
             const int d = (R + k) / R;
@@ -304,13 +346,18 @@ struct GroupVoxel {
     }
 };
 
-template <typename real, int R, int KMAX, int G, bool LEAN>
+template <int R, int KMAX, int G>
+__host__ __device__ constexpr int fastg_halo_buf() { return 2 * ((KMAX + 3) & ~3) + G * R; }
+
+template <typename real, int R, int KMAX, int G, bool LEAN, bool SMH = false>
 __host__ __device__ constexpr size_t fastg_warp_bytes() {
     return (size_t)(32 / G) * pb_scratch_doubles(KMAX) * sizeof(double) +
-           (LEAN ? ((size_t)R * 32 + (size_t)(32 / G) * KMAX) * sizeof(real) : 0);
+           (LEAN ? ((size_t)R * 32 + (size_t)(32 / G) * KMAX) * sizeof(real) : 0) +
+           (SMH ? (size_t)2 * (32 / G) * fastg_halo_buf<R, KMAX, G>() * sizeof(real) : 0);
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
+          bool SMH = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_bdg_kernel(BdArgs<real> p) {
     constexpr int VPW = 32 / G;
@@ -320,7 +367,7 @@ fast_bdg_kernel(BdArgs<real> p) {
     real *beta = reinterpret_cast<real *>(smem);
     const size_t beta_bytes = ((size_t)p.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     fill_momentum_table(beta, p.nb_iter);
-    unsigned char *wbase = smem + beta_bytes + (size_t)warp * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
+    unsigned char *wbase = smem + beta_bytes + (size_t)warp * fastg_warp_bytes<real, R, KMAX, G, LEAN, SMH>();
     ThetaScratch scs[VPW];
 #pragma unroll
     for (int g = 0; g < VPW; ++g)
@@ -331,8 +378,16 @@ fast_bdg_kernel(BdArgs<real> p) {
         if (grp == g) sc = scs[g];
     const int T = p.T, K = p.K, ntr = p.nb_iter + 2;
 
-    GroupVoxel<real, R, KMAX, G, TAIL, 1, LEAN> vx;
+    GroupVoxel<real, R, KMAX, G, TAIL, 1, LEAN, SMH> vx;
     vx.init(lane, T);
+    if (SMH) {
+        constexpr int PADH = (KMAX + 3) & ~3, BUFV = fastg_halo_buf<R, KMAX, G>();
+        real *hb = reinterpret_cast<real *>(wbase + fastg_warp_bytes<real, R, KMAX, G, LEAN, false>());
+        for (int i = lane; i < 2 * VPW * BUFV; i += 32) hb[i] = real(0);   // zero pads (and slots)
+        vx.myA = hb + grp * BUFV + PADH + vx.q * R;
+        vx.myB = hb + (VPW + grp) * BUFV + PADH + vx.q * R;
+        __syncwarp();
+    }
     if (LEAN) {
         real *lean = reinterpret_cast<real *>(wbase + (size_t)VPW * pb_scratch_doubles(KMAX) * sizeof(double));
         vx.h_s = lean + grp * KMAX;
@@ -499,12 +554,13 @@ int fast_wave_voxels(Kern kern, int threads, size_t smem, int voxels_per_cta) {
     return sms * occ * voxels_per_cta;
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
+          bool SMH = false>
 int fast_bdg_wave(int nb_iter) {
     const size_t beta_bytes = ((size_t)nb_iter * sizeof(real) + 15) & ~(size_t)15;
-    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
-    return fast_wave_voxels(fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN>, WARPS * 32, smem,
-                            WARPS * (32 / G));
+    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN, SMH>();
+    return fast_wave_voxels(fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>, WARPS * 32,
+                            smem, WARPS * (32 / G));
 }
 
 template <int R, int KMAX, int G, int TAIL>
@@ -512,12 +568,13 @@ bool fastg_shape_ok(int T, int K) {
     return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
+          bool SMH = false>
 int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
     constexpr int VPW = 32 / G;
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
-    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN>();
-    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN>;
+    const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN, SMH>();
+    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>;
     int dev = 0, sms = 0, max_smem = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;

@@ -98,11 +98,11 @@ void run32(const char *name, Bufs &b, int nb_iter, bool is_ref) {
     const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * pb_scratch_doubles(KMAX) * 8;
     time_it(name, b, [&] { return fast_bd_launch<float, R, KMAX, CIRC, WARPS, MINB>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
-template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false>
+template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false, bool SMH = false>
 void rung(const char *name, Bufs &b, int nb_iter, bool is_ref = false) {
-    auto kern = fast_bdg_kernel<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>;
-    const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * fastg_warp_bytes<float, R, KMAX, G, LEAN>();
-    time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
+    auto kern = fast_bdg_kernel<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>;
+    const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * fastg_warp_bytes<float, R, KMAX, G, LEAN, SMH>();
+    time_it(name, b, [&] { return fast_bdg_launch<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
 
 template <int R, int KMAX, int NW, int MINB>
@@ -116,14 +116,13 @@ int main(int argc, char **argv) {
     const int set = argc > 1 ? atoi(argv[1]) : 0;
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
-        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
-        rung<19, 20, 16, 8, 5, 3>("G16 R19 K20 T8 W5 M3", b, 100);
-        rung<19, 20, 16, 8, 8, 2>("G16 R19 K20 T8 W8 M2", b, 100);
-        rung<19, 20, 16, 8, 4, 4, true>("G16 R19 K20 T8 W4 M4 LEAN", b, 100);
-        rung<19, 20, 16, 8, 5, 3, true>("G16 R19 K20 T8 W5 M3 LEAN", b, 100);
-        rung<19, 20, 16, 8, 4, 3, true>("G16 R19 K20 T8 W4 M3 LEAN", b, 100);
-        rung<19, 20, 16, 4, 4, 3>("G16 R19 K20 T4 W4 M3", b, 100);
-        rung<10, 20, 32, 10, 4, 5>("G32 R10 K20 T10 W4 M5", b, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3 (ref)", b, 100, true);
+        rung<20, 20, 16, 20, 4, 3, false, true>("G16 R20 K20 W4 M3 SMH", b, 100);
+        rung<20, 20, 16, 20, 4, 4, false, true>("G16 R20 K20 W4 M4 SMH", b, 100);
+        rung<20, 20, 16, 20, 2, 6, false, true>("G16 R20 K20 W2 M6 SMH", b, 100);
+        rung<12, 20, 32, 12, 4, 4, false, true>("G32 R12 K20 W4 M4 SMH", b, 100);
+        rung<12, 20, 32, 12, 4, 5, false, true>("G32 R12 K20 W4 M5 SMH", b, 100);
+        rung<40, 20, 8, 40, 4, 2, false, true>("G8 R40 K20 W4 M2 SMH", b, 100);
         b.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
