@@ -116,13 +116,7 @@ int main(int argc, char **argv) {
     const int set = argc > 1 ? atoi(argv[1]) : 0;
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
-        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3 (ref)", b, 100, true);
-        rung<20, 20, 16, 20, 4, 3, false, true>("G16 R20 K20 W4 M3 SMH", b, 100);
-        rung<20, 20, 16, 20, 4, 4, false, true>("G16 R20 K20 W4 M4 SMH", b, 100);
-        rung<20, 20, 16, 20, 2, 6, false, true>("G16 R20 K20 W2 M6 SMH", b, 100);
-        rung<12, 20, 32, 12, 4, 4, false, true>("G32 R12 K20 W4 M4 SMH", b, 100);
-        rung<12, 20, 32, 12, 4, 5, false, true>("G32 R12 K20 W4 M5 SMH", b, 100);
-        rung<40, 20, 8, 40, 4, 2, false, true>("G8 R40 K20 W4 M2 SMH", b, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
         b.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
