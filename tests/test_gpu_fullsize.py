@@ -35,10 +35,8 @@ def test_cfg3_full_batch_permutation_and_batch_independence():
     for v in (0, 49999, V - 1):
         xo, zo, wo, ho, do = orc.bd(y[v].double().cpu().numpy(), 1.0, lbda=1.7, theta_0=2.0,
                                     nb_iter=100, theta_solver="exact")
-        assert abs(float(d["theta"][v]) - float(orc.theta_step_exact(
-            2.0, zo, y[v].double().cpu().numpy(), 1.0, 20.0, [(0.6, 1.9)])) ) < 1.0  # sanity only
-        assert rel(z[v].cpu().numpy(), zo) < 1e-3
-        assert rel(h[v].cpu().numpy(), ho) < 1e-3
+        assert rel(z[v].cpu().numpy(), zo) < 1e-4
+        assert rel(h[v].cpu().numpy(), ho) < 1e-4
         assert rel(d["J"][v].cpu().numpy(), do["J"]) < 1e-4
 
 
@@ -54,7 +52,7 @@ def test_cfg4_share_fp32_vs_fp64_and_permutation():
     for i, v in enumerate(sub.tolist()):
         assert abs(float(d["theta"][v]) - float(d64["theta"][i])) < 1e-4
         assert rel(d["J"][v].cpu().numpy(), d64["J"][i].cpu().numpy()) < 1e-4
-        assert rel(z[v].cpu().numpy(), z64[i].cpu().numpy()) < 2e-3
+        assert rel(z[v].cpu().numpy(), z64[i].cpu().numpy()) < 1e-4
     x2, z2, _, _, _ = pb.bd(y[sub].contiguous(), t_r, lbda=1.7, theta_0=2.0, nb_iter=100)
     assert torch.equal(z2, z[sub])
 
