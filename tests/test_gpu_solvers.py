@@ -231,3 +231,37 @@ def test_bd_streamed_host_batch_equals_single_launch():
         assert np.array_equal(u, v.cpu().numpy())
     for k in ("J", "r", "g", "theta", "n_trace"):
         assert np.array_equal(a[4][k], b[4][k].cpu().numpy()), k
+
+
+def test_deconv_auto_lambda_vs_oracle():
+    """deconv(lbda=None) (row N1): noise-constrained lambda loop with sigma supplied, against the
+    oracle restatement of pybold/bold_signal.py:99-214 (survey: matches the reference at 1e-16)."""
+    import pybold_b200 as pb
+    T = 200
+    y = gen_voxels(2, T, 1.0, 20.0, seed0=8000)
+    h, _ = orc.spm_hrf(1.2, 1.0, 20.0, True)
+    x0 = np.random.RandomState(1).randn(T)
+    sigma = 0.3
+    for es in (False, True):
+        x, z, dz, J, R, G = pb.deconv(y[0], 1.0, h, lbda=None, nb_iter=8, nb_sub_iter=40,
+                                      early_stopping=es, tol=1e-3, x0=x0, sigma=sigma)
+        xo, zo, wo, Jo, Ro, Go, _ = orc.deconv_auto_lbda(y[0], h, sigma, x0_power=x0, early_stopping=es,
+                                                         tol=1e-3, nb_iter=8, nb_sub_iter=40)
+        assert len(J) == len(Jo) and isinstance(J, list)
+        assert rel(dz, wo) < 1e-9 and rel(z, zo) < 1e-9 and rel(x, xo) < 1e-9
+        assert rel(J, Jo) < 1e-9 and rel(R, Ro) < 1e-9 and rel(G, Go) < 1e-9
+    # batched: both voxels at once equal the one-by-one runs
+    xb, zb, dzb, Jb, Rb, Gb = pb.deconv(y, 1.0, h, lbda=None, nb_iter=5, nb_sub_iter=30,
+                                        early_stopping=False, x0=x0, sigma=sigma)
+    x1, z1, dz1, J1, R1, G1 = pb.deconv(y[1], 1.0, h, lbda=None, nb_iter=5, nb_sub_iter=30,
+                                        early_stopping=False, x0=x0, sigma=sigma)
+    assert rel(zb[1], z1) < 1e-12 and rel(Jb[1], J1) < 1e-12
+
+
+def test_noise_estimate_matches_oracle_restatement():
+    """db3 MAD sigma (unpinned against PyWavelets): device == oracle restatement."""
+    from pybold_b200.noise import mad_daub_noise_est
+    y = gen_voxels(5, 301, 1.0, 20.0, seed0=8100)
+    got = mad_daub_noise_est(torch.as_tensor(y, device="cuda")).cpu().numpy()
+    want = np.array([orc.mad_daub_noise_est(v) for v in y])
+    assert np.max(np.abs(got / want - 1)) < 1e-12
