@@ -44,6 +44,12 @@ def algorithmic_flops_per_voxel(T, K, n):
     return (n + 1) * n * f_it + (n + 1) * f_j + n * f_mom
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the solver kernel, from the committed
+# `ncu --set full` capture of this very command (profiles/r01_ncu_bd_t300_final.txt); only valid for
+# the default workload, null otherwise.
+NCU_TRAFFIC_BYTES = {(100000, 300, 100): 738.4e6}
+
+
 def algorithmic_bytes_per_voxel(T, K, n):
     return 4 * (T + 3 * T + K + 1 + 3 * (n + 2) + 1)
 
@@ -320,7 +326,9 @@ def main():
         nominal = sms * 128 * 2 * sm_max * 1e6 / 1e12
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": fma_tflops, "unit": "TFLOP/s",
-            "frac": achieved / fma_tflops, "traffic": None,
+            "frac": achieved / fma_tflops, "traffic": NCU_TRAFFIC_BYTES.get((V, T, n)),
+            "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_bd_t300_final.txt); "
+                            "algorithmic %.1f MB" % (hbm_bytes / 1e6),
             "peak_source": "FFMA microbenchmark in this run (pb_bench_fma_f32); nominal "
                            "%d SMs x 128 lanes x 2 x %.0f MHz = %.1f" % (sms, sm_max, nominal),
             "frac_of_nominal": achieved / nominal,
