@@ -28,7 +28,7 @@ import numpy as np
 from scipy.optimize import fmin_l_bfgs_b
 from scipy.stats import gamma as _gamma
 
-THETA_XTOL = 1.0e-12   # step tolerance of the exact theta solver (same constant on the device)
+THETA_XTOL = 1.0e-10   # step tolerance of the exact theta solver (same constant on the device)
 MIN_DELTA = 0.5   # pybold/hrf_model.py:8
 MAX_DELTA = 2.0   # pybold/hrf_model.py:9
 

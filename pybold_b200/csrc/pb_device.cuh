@@ -13,11 +13,11 @@
 #include <stdint.h>
 
 #define PB_FULL 0xffffffffu
-// Newton on f'(theta) stops when the step falls below this (relative to max(1, |theta|)).  The
-// evaluation noise of f' (double rounding of M h - b) puts a floor of ~1e-14 on the step, so a
-// tighter tolerance would only burn the iteration cap; the reference's own L-BFGS-B answer is
-// ~1e-8 away from the minimiser.
-#define PB_THETA_XTOL 1.0e-12
+// Newton on f'(theta) stops when the step just taken falls below this (relative to max(1, |theta|)).
+// In the Newton regime the error after such a step is its square (~1e-20); only a bisection ending
+// is limited to 1e-10.  The evaluation noise of f' (double rounding of M h - b) puts a floor of
+// ~1e-14 on the step anyway, and the reference's own L-BFGS-B answer is ~1e-8 away from the minimiser.
+#define PB_THETA_XTOL 1.0e-10
 
 namespace pb {
 
