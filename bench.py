@@ -342,7 +342,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cores = min(os.cpu_count() or 1, 64)
-            n_s = cores * 2
+            n_s = cores * 6
             y_s = y_host[:n_s].numpy().astype(np.float64)
             rate, dt = cpu_oracle_rate(y_s, w, cores)
             cpu = {"value": rate, "unit": "voxels/s", "cores": cores, "kind": "port",

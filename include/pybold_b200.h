@@ -164,6 +164,13 @@ int pb_hrf_estim_f64(const double *z, const double *y, double t_r, double hrf_du
                      double *out_theta, double *out_h, double *out_cost,
                      int64_t V, int T, int K, pb_stream_t stream);
 
+/* ---- N4: layout adapter between the reference pipeline's time-major voxel matrices [T, V]
+ * (`NiftiMasker.fit_transform`, consumed as `voxels.T`, examples/icassp_2019/validation.py:90-103)
+ * and the solvers' [V, T]: out[c, r] = in[r, c] for an in[rows, cols] row-major matrix.  Out of place
+ * (in != out); rows <= 2 097 120. */
+int pb_transpose_f32(const float *in, float *out, int64_t rows, int64_t cols, pb_stream_t stream);
+int pb_transpose_f64(const double *in, double *out, int64_t rows, int64_t cols, pb_stream_t stream);
+
 /* ---- measurement utility (not part of the reference API) --------------------------------
  * FP32 FMA-pipe microbenchmark used as the roofline denominator: launches
  * `blocks` CTAs of 256 threads, each thread running 8 independent chains of `iters` FFMA.

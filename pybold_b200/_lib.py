@@ -53,6 +53,7 @@ _OPS = {
     "pb_bd": [_P, c_double, c_double, _P, c_int64, _P, c_int64, _P, c_double, c_double,
               c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
               c_int64, c_int, c_int, _P],
+    "pb_transpose": [_P, _P, c_int64, c_int64, _P],
     "pb_hrf_estim": [_P, _P, c_double, c_double, _P, c_int64, c_double, c_double, _P, _P, _P,
                      c_int64, c_int, c_int, _P],
 }

@@ -168,6 +168,17 @@ int run_lipschitz_frob(const real *h, int64_t h_stride, real *out_L, int64_t V, 
 }
 
 template <typename real>
+int run_transpose(const real *in, real *out, int64_t rows, int64_t cols, pb_stream_t stream) {
+    if (rows == 0 || cols == 0) return PB_OK;
+    if (!in || !out || rows < 0 || cols < 0 || in == out) return PB_ERR_INVALID_ARG;
+    const int64_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+    if (gy > 65535 || gx > 2147483647LL) return PB_ERR_UNSUPPORTED;
+    pb::transpose_kernel<real><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        in, out, rows, cols);
+    return last_error();
+}
+
+template <typename real>
 int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
     if (a.V == 0) return PB_OK;
     if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz || !a.out_J ||
@@ -355,6 +366,9 @@ int pb_hrf_len(double t_r, double dur) {
         a.out_theta = out_theta; a.out_J = out_J; a.out_r = out_r; a.out_g = out_g;                    \
         a.out_ntrace = out_ntrace; a.V = V; a.T = T; a.K = K;                                          \
         return run_bd<REAL>(a, t_r, hrf_dur, s);                                                       \
+    }                                                                                                  \
+    int pb_transpose_##SUF(const REAL *in, REAL *out, int64_t rows, int64_t cols, pb_stream_t s) {    \
+        return run_transpose<REAL>(in, out, rows, cols, s);                                            \
     }                                                                                                  \
     int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
                            const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \

@@ -20,10 +20,11 @@ const FastEntry<real> *fast_table(int *n);
 // group variants (pb_fastg.cuh): several voxels per warp, bd without early stopping only
 template <typename real>
 struct FastGEntry {
-    int R, KMAX, G;
+    int R, KMAX, G, TAIL;
     bool (*ok)(int T, int K);
     int (*bd)(const BdArgs<real> &, cudaStream_t);
     int (*wave)(int nb_iter);
+    int (*deconv)(const DeconvArgs<real> &, cudaStream_t);   // null for CTA variants
 };
 
 template <typename real>
@@ -59,12 +60,12 @@ static const FastGEntry<real> *pick_group(int T, int K) {
     const FastGEntry<real> *t = fastc_table<real>(&n);
     const FastGEntry<real> *best = nullptr;
     for (int i = 0; i < n; ++i)
-        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G < best->R * best->KMAX * best->G))
+        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL < best->R * best->KMAX * best->G * 64 + best->TAIL))
             best = &t[i];
     if (best) return best;
     t = fastg_table<real>(&n);
     for (int i = 0; i < n; ++i)
-        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G < best->R * best->KMAX * best->G))
+        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL < best->R * best->KMAX * best->G * 64 + best->TAIL))
             best = &t[i];
     return best;
 }
@@ -84,14 +85,28 @@ static int bd_dispatch(const BdArgs<real> &a, cudaStream_t s) {
     return e ? e->bd(a, s) : FAST_NO_MATCH;
 }
 
-int fast_deconv_dispatch(const DeconvArgs<float> &a, cudaStream_t s) {
-    const FastEntry<float> *e = pick<float>(a.T, a.K);
+template <typename real>
+static int deconv_dispatch(const DeconvArgs<real> &a, cudaStream_t s) {
+    static const bool no_group = getenv("PB_DISABLE_GROUP") != nullptr;
+    if (!(a.early_stopping && a.wind >= 2) && !no_group) {
+        int n = 0;
+        const FastGEntry<real> *t = fastg_table<real>(&n);
+        const FastGEntry<real> *best = nullptr;
+        for (int i = 0; i < n; ++i)
+            if (t[i].deconv && t[i].ok(a.T, a.K) &&
+                (!best || t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL < best->R * best->KMAX * best->G * 64 + best->TAIL))
+                best = &t[i];
+        if (best) {
+            const int rc = best->deconv(a, s);
+            if (rc != FAST_NO_MATCH) return rc;
+        }
+    }
+    const FastEntry<real> *e = pick<real>(a.T, a.K);
     return e ? e->deconv(a, s) : FAST_NO_MATCH;
 }
-int fast_deconv_dispatch(const DeconvArgs<double> &a, cudaStream_t s) {
-    const FastEntry<double> *e = pick<double>(a.T, a.K);
-    return e ? e->deconv(a, s) : FAST_NO_MATCH;
-}
+
+int fast_deconv_dispatch(const DeconvArgs<float> &a, cudaStream_t s) { return deconv_dispatch<float>(a, s); }
+int fast_deconv_dispatch(const DeconvArgs<double> &a, cudaStream_t s) { return deconv_dispatch<double>(a, s); }
 int fast_bd_dispatch(const BdArgs<float> &a, cudaStream_t s) { return bd_dispatch<float>(a, s); }
 int fast_bd_dispatch(const BdArgs<double> &a, cudaStream_t s) { return bd_dispatch<double>(a, s); }
 

@@ -563,6 +563,99 @@ int fast_bdg_wave(int nb_iter) {
                             smem, WARPS * (32 / G));
 }
 
+// ------------------------------------------------------------------------------------------------
+// deconv, fixed lambda, no early stopping (pybold/bold_signal.py:49-97), group layout.
+// Taps are the caller's (tap 0 is not assumed zero); J_k is taken from the residual that iteration
+// k+1 forms anyway (two segmented sums per iteration).
+// ------------------------------------------------------------------------------------------------
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fast_deconvg_kernel(DeconvArgs<real> p) {
+    constexpr int VPW = 32 / G;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G;
+    real *beta = reinterpret_cast<real *>(smem);
+    fill_momentum_table(beta, p.nb_iter);
+    const int T = p.T, K = p.K;
+    GroupVoxel<real, R, KMAX, G, TAIL, 0> vx;
+    vx.init(lane, T);
+    const int q = vx.q;
+    for (int64_t v0 = ((int64_t)blockIdx.x * WARPS + warp) * VPW; v0 < p.V;
+         v0 += (int64_t)gridDim.x * WARPS * VPW) {
+        const bool on = v0 + grp < p.V;
+        const int64_t v = on ? v0 + grp : p.V - 1;
+        const real *yv = p.y + v * T;
+        const real *hv = p.h + v * p.h_stride;
+        vx.set_dy(yv, T);
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) vx.h[j] = j < K ? hv[j] : real(0);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = q * R + r;
+            vx.w[r] = (p.w0 && i < T) ? p.w0[v * T + i] : real(0);
+        }
+        const double Lc = (double)p.L[v * p.L_stride];
+        const double lam = (double)p.lbda[v * p.lbda_stride];
+        const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
+        real *Jv = p.out_J + v * (int64_t)p.nb_iter;
+        const bool writer = on && q == 0;
+        real res[R];
+        for (int k = 0; k < p.nb_iter; ++k) {
+            vx.forward(res);
+            if (k > 0) {
+                const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
+                                 lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+                if (writer) Jv[k - 1] = (real)J;
+            }
+            real g[R];
+            vx.adjoint(res, g);
+            vx.update(g, step, th, beta[k]);
+        }
+        vx.forward(res);
+        {
+            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
+                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            if (writer) Jv[p.nb_iter - 1] = (real)J;
+        }
+        real y[R], z[R];
+        vx.load_y(yv, T, y);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            y[r] += res[r];
+            z[r] = vx.w[r];
+        }
+        vx.scan_fwd(z);
+        vx.store(p.out_x + v * T, y, T, on);
+        vx.store(p.out_z + v * T, z, T, on);
+        vx.store(p.out_dz + v * T, vx.w, T, on);
+        if (writer) p.out_niter[v] = p.nb_iter;
+        __syncwarp();
+    }
+}
+
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+int fast_deconvg_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
+    constexpr int VPW = 32 / G;
+    const size_t smem = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    auto kern = fast_deconvg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB>;
+    int dev = 0, sms = 0, occ = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return FAST_NO_MATCH;
+    const int64_t per_cta = (int64_t)WARPS * VPW;
+    const int64_t need = (a.V + per_cta - 1) / per_cta;
+    const int64_t cap = (int64_t)sms * occ;
+    kern<<<(int)(need < cap ? need : cap), WARPS * 32, smem, stream>>>(a);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <int R, int KMAX, int G, int TAIL>
 bool fastg_shape_ok(int T, int K) {
     return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;

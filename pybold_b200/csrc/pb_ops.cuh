@@ -128,6 +128,28 @@ __global__ void lipschitz_frob_kernel(const real *h, int64_t h_stride, real *out
     }
 }
 
+// Layout adapter (row N4 of SURVEY.md 8(f)): the ingest side of the reference pipeline holds voxel
+// matrices time-major, [T, V] (NiftiMasker.fit_transform, examples/icassp_2019/validation.py:90-103,
+// consumed as `voxels.T`); the solvers want [V, T].  32 x 32 tiles through padded shared memory:
+// coalesced 128-byte rows on both sides, HBM bound (2 x 4 bytes per sample).
+template <typename real>
+__global__ void transpose_kernel(const real *in, real *out, int64_t rows, int64_t cols) {
+    __shared__ real tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8 threads
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int64_t r = r0 + ty + k, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + k][tx] = in[r * cols + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int64_t c = c0 + ty + k, r = r0 + tx;
+        if (r < rows && c < cols) out[c * rows + r] = tile[tx][ty + k];
+    }
+}
+
 // hrf_estim / the theta step alone (pybold/bold_signal.py:217-239, :329-334)
 template <typename real>
 __global__ void hrf_estim_kernel(const real *z, const real *y, HrfGrid grid, const real *theta0,

@@ -121,3 +121,19 @@ def test_abi_error_codes():
     assert _lib.lib.pb_integ_op_f64(x.data_ptr(), x.data_ptr(), 0, 8, 0) == 0      # empty batch is fine
     with pytest.raises(ValueError):
         _lib.check(_lib.PB_ERR_UNSUPPORTED, "x")
+
+
+def test_layout_adapter_roundtrip_and_ragged_tiles():
+    """[T, V] <-> [V, T] transpose kernel (row N4): exact, including partial 32 x 32 tiles."""
+    from pybold_b200.io import timeseries_from_voxels, voxels_from_timeseries
+    rng = np.random.RandomState(2)
+    for (T, V, dt) in [(1, 1, np.float64), (33, 65, np.float32), (300, 1001, np.float32),
+                       (1200, 4097, np.float64)]:
+        a = rng.randn(T, V).astype(dt)
+        vt = voxels_from_timeseries(a)
+        assert vt.is_cuda and vt.shape == (V, T) and vt.is_contiguous()
+        assert np.array_equal(vt.cpu().numpy(), a.T)
+        back = timeseries_from_voxels(vt)
+        assert np.array_equal(back.cpu().numpy(), a)
+    with pytest.raises(ValueError):
+        voxels_from_timeseries(np.zeros(5))

@@ -172,7 +172,9 @@ def test_hrf_estim_vs_exact_minimiser(golden):
 
 
 @pytest.mark.parametrize("T,t_r", [(296, 1.0), (299, 1.0), (304, 1.0), (233, 0.75), (305, 1.0), (64, 1.0),
-                                   (600, 1.0), (585, 1.0), (640, 0.75), (1195, 0.72), (1280, 0.72)])
+                                   (600, 1.0), (585, 1.0), (640, 0.75), (1195, 0.72), (1280, 0.72),
+                                   (284, 0.7535), (200, 1.0), (209, 0.72), (320, 0.72), (400, 1.0),
+                                   (500, 0.72), (700, 0.72), (900, 0.72)])
 def test_bd_kernel_variants_tail_shapes(T, t_r):
     """Shapes at the edges of the register-tiled variants (group kernel tail, CTA kernel with one
     and two warps per voxel, linear kernel, short series), odd batch so that one group of the last
@@ -180,12 +182,12 @@ def test_bd_kernel_variants_tail_shapes(T, t_r):
     import pybold_b200 as pb
     from pybold_b200 import _lib
     V = 3
-    n_it = 15 if T < 1000 else 6
+    n_it = 15 if T < 650 else 6
     y = gen_voxels(V, T, t_r, 20.0, seed0=5000 + T)
     x, z, dz, h, d = pb.bd(y, t_r, lbda=1.2, theta_0=2.0, hrf_dur=20.0, nb_iter=n_it)
     assert _lib.lib.pb_solver_variant(T, h.shape[1], 1) != 0
     for v in range(V):
-        if T > 1000 and v > 0:
+        if T > 650 and v > 0:
             continue            # the dense T^3 oracle is slow at this size
         xo, zo, wo, ho, do = orc.bd(y[v], t_r, lbda=1.2, theta_0=2.0, hrf_dur=20.0, nb_iter=n_it,
                                     theta_solver="exact")
