@@ -28,7 +28,10 @@ import numpy as np
 from scipy.optimize import fmin_l_bfgs_b
 from scipy.stats import gamma as _gamma
 
-THETA_XTOL = 1.0e-10   # step tolerance of the exact theta solver (same constant on the device)
+# step tolerances of the exact theta solver (same constants on the device): a Newton step of size dx
+# leaves an error ~dx^2, a bisection step ~dx
+THETA_XTOL_NEWTON = 1.0e-7
+THETA_XTOL_BISECT = 1.0e-12
 MIN_DELTA = 0.5   # pybold/hrf_model.py:8
 MAX_DELTA = 2.0   # pybold/hrf_model.py:9
 
@@ -412,7 +415,7 @@ def bracketed_newton(gc, theta, lo, hi, max_iter=100):
         if x_new == x:
             return x
         x = x_new
-        if abs(dx) <= THETA_XTOL * max(1.0, abs(x)):
+        if abs(dx) <= (THETA_XTOL_NEWTON if newton_ok else THETA_XTOL_BISECT) * max(1.0, abs(x)):
             return x
         gx, cx = gc(x)
         if gx == 0.0:

@@ -13,11 +13,13 @@
 #include <stdint.h>
 
 #define PB_FULL 0xffffffffu
-// Newton on f'(theta) stops when the step just taken falls below this (relative to max(1, |theta|)).
-// In the Newton regime the error after such a step is its square (~1e-20); only a bisection ending
-// is limited to 1e-10.  The evaluation noise of f' (double rounding of M h - b) puts a floor of
-// ~1e-14 on the step anyway, and the reference's own L-BFGS-B answer is ~1e-8 away from the minimiser.
-#define PB_THETA_XTOL 1.0e-10
+// Stopping rule of the theta solver, on the step dx just taken (relative to max(1, |theta|)):
+//   after a Newton step the remaining error is ~dx^2 (quadratic convergence), so |dx| <= 1e-7 leaves
+//   ~1e-14; after a bisection step it is ~|dx|, so that needs |dx| <= 1e-12.
+// The evaluation noise of f' (double rounding of M h - b) puts a floor of ~1e-14 on dx anyway, and
+// the reference's own L-BFGS-B answer is ~1e-8 away from the minimiser.
+#define PB_THETA_XTOL_NEWTON 1.0e-7
+#define PB_THETA_XTOL_BISECT 1.0e-12
 
 namespace pb {
 
@@ -331,7 +333,7 @@ __device__ __forceinline__ double theta_solve_warp(double theta_prev, double lo,
                 if (x_new == x) break;
                 x = x_new;
                 result = x;
-                if (fabs(dx) <= PB_THETA_XTOL * fmax(1.0, fabs(x))) break;
+                if (fabs(dx) <= (newton_ok ? PB_THETA_XTOL_NEWTON : PB_THETA_XTOL_BISECT) * fmax(1.0, fabs(x))) break;
                 theta_eval_warp(x, grid, sc, lane, gx, cx);
                 ++evals;
                 if (gx == 0.0) break;

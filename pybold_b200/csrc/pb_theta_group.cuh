@@ -226,7 +226,10 @@ __device__ __forceinline__ double theta_solve_group(double theta_prev, double lo
             } else {
                 x = x_new;
                 result = x;
-                if (fabs(dx) <= PB_THETA_XTOL * fmax(1.0, fabs(x))) phase = DONE; else query = x;
+                if (fabs(dx) <= (newton_ok ? PB_THETA_XTOL_NEWTON : PB_THETA_XTOL_BISECT) * fmax(1.0, fabs(x)))
+                    phase = DONE;
+                else
+                    query = x;
             }
         }
         if (phase == DONE) query = result;
