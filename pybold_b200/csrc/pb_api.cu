@@ -96,7 +96,7 @@ int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V,
     if (V == 0) return PB_OK;
     DeviceInfo d = device_info();
     if (d.err) return d.err;
-    pb::GenLayout lay = pb::GenLayout::make(T, OP >= pb::OP_CONV ? K : 1, 0, false);
+    pb::OpLayout lay = pb::OpLayout::make(T, OP >= pb::OP_CONV ? K : 1);
     LaunchPlan p = plan_launch(d, 0, lay.warp_bytes(sizeof(real)), V, 8);
     if (!p.warps) return PB_ERR_UNSUPPORTED;
     auto kern = pb::op_kernel<real, OP>;

@@ -10,40 +10,148 @@ namespace pb {
 
 enum OpKind { OP_INTEG = 0, OP_INTEG_ADJ, OP_CONV, OP_CONV_ADJ, OP_HRFINTEG, OP_HRFINTEG_ADJ };
 
+// Row operators on a zero-framed shared-memory copy of the row, four samples per lane and step:
+//   scans: in-vector prefix + 5-step shuffle scan of the vector totals + running carry;
+//   K-tap convolution / correlation: each lane makes 4 outputs from 16-byte window loads
+//   (16 FMA per load) instead of K scalar loads per output.
+template <typename real>
+struct alignas(4 * sizeof(real) > 16 ? 16 : 4 * sizeof(real)) RowVec4 { real t[4]; };
+
+struct OpLayout {
+    int pad;     // zero frame before and after the row, >= K + 3, multiple of 4
+    int tp;      // row length rounded up to 128 (zero filled)
+    int hp;      // padded tap buffer: 3 + K rounded + 8
+    __host__ __device__ static OpLayout make(int T, int K) {
+        OpLayout l;
+        l.pad = (K + 3 + 3) & ~3;
+        l.tp = (T + 127) & ~127;
+        l.hp = ((K + 3) & ~3) + 12;
+        return l;
+    }
+    __host__ __device__ int row() const { return 2 * pad + tp; }
+    __host__ __device__ size_t warp_bytes(size_t rs) const { return ((size_t)2 * row() + hp) * rs; }
+};
+
+template <typename real>
+__device__ __forceinline__ void row_scan_fwd(real *a, int tp, int lane) {   // a = first sample
+    real carry = 0;
+    for (int base = 0; base < tp; base += 128) {
+        RowVec4<real> v = *reinterpret_cast<RowVec4<real> *>(a + base + 4 * lane);
+        v.t[1] += v.t[0];
+        v.t[2] += v.t[1];
+        v.t[3] += v.t[2];
+        real inc = v.t[3];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const real t = __shfl_up_sync(PB_FULL, inc, d);
+            if (lane >= d) inc += t;
+        }
+        real ex = __shfl_up_sync(PB_FULL, inc, 1);
+        ex = (lane == 0 ? real(0) : ex) + carry;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v.t[e] += ex;
+        *reinterpret_cast<RowVec4<real> *>(a + base + 4 * lane) = v;
+        carry += __shfl_sync(PB_FULL, inc, 31);
+    }
+    __syncwarp();
+}
+
+template <typename real>
+__device__ __forceinline__ void row_scan_rev(real *a, int tp, int lane) {
+    real carry = 0;
+    for (int base = tp - 128; base >= 0; base -= 128) {
+        RowVec4<real> v = *reinterpret_cast<RowVec4<real> *>(a + base + 4 * lane);
+        v.t[2] += v.t[3];
+        v.t[1] += v.t[2];
+        v.t[0] += v.t[1];
+        real inc = v.t[0];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const real t = __shfl_down_sync(PB_FULL, inc, d);
+            if (lane + d < 32) inc += t;
+        }
+        real ex = __shfl_down_sync(PB_FULL, inc, 1);
+        ex = (lane == 31 ? real(0) : ex) + carry;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v.t[e] += ex;
+        *reinterpret_cast<RowVec4<real> *>(a + base + 4 * lane) = v;
+        carry += __shfl_sync(PB_FULL, inc, 0);
+    }
+    __syncwarp();
+}
+
+// out[i] = sum_j h[j] in[i - j] (ADJ = false) or sum_j h[j] in[i + j] (ADJ = true); hp[3 + j] = h[j]
+template <typename real, bool ADJ>
+__device__ __forceinline__ void row_conv(const real *in, real *out, const real *hp, int tp, int K,
+                                         int lane) {
+    const int nc = (K + 3 + 3) / 4;
+    for (int base = 0; base < tp; base += 128) {
+        const int i0 = base + 4 * lane;
+        real acc[4] = {0, 0, 0, 0};
+        for (int c = 0; c < nc; ++c) {
+            const RowVec4<real> xv = *reinterpret_cast<const RowVec4<real> *>(in + (ADJ ? i0 + 4 * c : i0 - 4 * c));
+            const RowVec4<real> h0 = *reinterpret_cast<const RowVec4<real> *>(hp + 4 * c);
+            const RowVec4<real> h1 = *reinterpret_cast<const RowVec4<real> *>(hp + 4 * c + 4);
+            real hh[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                hh[e] = h0.t[e];
+                hh[4 + e] = h1.t[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int t = 0; t < 4; ++t) acc[e] = fma(hh[3 + (ADJ ? t - e : e - t)], xv.t[t], acc[e]);
+        }
+        RowVec4<real> o;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o.t[e] = acc[e];
+        *reinterpret_cast<RowVec4<real> *>(out + i0) = o;
+    }
+    __syncwarp();
+}
+
 template <typename real, int OP>
 __global__ void op_kernel(const real *h, int64_t h_stride, const real *x, real *out, int64_t V,
-                          int T, int K, GenLayout lay) {
+                          int T, int K, OpLayout lay) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    double *scratch;
-    GenVoxel<real> g = gen_bind<real>(smem + (size_t)warp * lay.warp_bytes(sizeof(real)), lay, T, K,
-                                      lane, scratch);
+    real *bufA = reinterpret_cast<real *>(smem + (size_t)warp * lay.warp_bytes(sizeof(real)));
+    real *bufB = bufA + lay.row();
+    real *hp = bufB + lay.row();
+    real *A = bufA + lay.pad, *B = bufB + lay.pad;
+    for (int i = lane; i < 2 * lay.row() + lay.hp; i += 32) bufA[i] = real(0);   // zero frames
+    __syncwarp();
     for (int64_t v = (int64_t)blockIdx.x * nwarp + warp; v < V; v += (int64_t)gridDim.x * nwarp) {
-        for (int i = lane; i < T; i += 32) g.as[i] = x[v * T + i];
-        if (OP >= OP_CONV)
-            for (int a = lane; a < K; a += 32) g.hr[a] = h[v * h_stride + a];
+        for (int i = lane; i < T; i += 32) A[i] = x[v * T + i];
+        if (OP == OP_HRFINTEG)      // a previous scan left the running total in the zero fill
+            for (int i = T + lane; i < lay.tp; i += 32) A[i] = real(0);
+        if (OP >= OP_CONV && (h_stride != 0 || v == (int64_t)blockIdx.x * nwarp + warp))
+            for (int a = lane; a < K; a += 32) hp[3 + a] = h[v * h_stride + a];
         __syncwarp();
-        real *res = g.as;
+        real *res = A;
         if (OP == OP_INTEG) {
-            g.scan_fwd(g.as);
+            row_scan_fwd(A, lay.tp, lane);
         } else if (OP == OP_INTEG_ADJ) {
-            g.scan_rev(g.as);
+            row_scan_rev(A, lay.tp, lane);
         } else if (OP == OP_CONV) {
-            g.conv(g.as, nullptr, g.bs);
-            res = g.bs;
+            row_conv<real, false>(A, B, hp, lay.tp, K, lane);
+            res = B;
         } else if (OP == OP_CONV_ADJ) {
-            g.corr(g.as, g.bs);
-            res = g.bs;
+            row_conv<real, true>(A, B, hp, lay.tp, K, lane);
+            res = B;
         } else if (OP == OP_HRFINTEG) {
-            g.scan_fwd(g.as);
-            g.conv(g.as, nullptr, g.bs);
-            res = g.bs;
+            row_scan_fwd(A, lay.tp, lane);
+            row_conv<real, false>(A, B, hp, lay.tp, K, lane);
+            res = B;
         } else {
-            g.corr(g.as, g.bs);
-            g.scan_rev(g.bs);
-            res = g.bs;
+            row_conv<real, true>(A, B, hp, lay.tp, K, lane);
+            row_scan_rev(B, lay.tp, lane);
+            res = B;
         }
         for (int i = lane; i < T; i += 32) out[v * T + i] = res[i];
+        if (OP == OP_INTEG || OP == OP_INTEG_ADJ)   // restore the zero fill beyond T for the next row
+            for (int i = T + lane; i < lay.tp; i += 32) A[i] = real(0);
         __syncwarp();
     }
 }
