@@ -117,10 +117,9 @@ int main(int argc, char **argv) {
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
+        rung<19, 20, 16, 8, 4, 4>("G16 R19 K20 T8 W4 M4", b, 100);
+        rung<19, 20, 16, 8, 4, 2>("G16 R19 K20 T8 W4 M2", b, 100);
         b.free_all();
-        Bufs c; c.alloc(42624, 240, 0.75, 100);
-        rung<15, 28, 16, 8, 4, 3>("G16 R15 K28 T8 W4 M3", c, 100, true);
-        c.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
         run32<20, 20, true, 4, 3>("G32 R20 K20 circ W4 M3 (ref)", b, 100, true);
