@@ -270,3 +270,22 @@ def test_noise_estimate_matches_oracle_restatement():
     got = mad_daub_noise_est(torch.as_tensor(y, device="cuda")).cpu().numpy()
     want = np.array([orc.mad_daub_noise_est(v) for v in y])
     assert np.max(np.abs(got / want - 1)) < 1e-12
+
+
+def test_inner_loop_stage_vs_reference_numba_golden(golden):
+    """Stage-wise gate of the 1e-9 FP64 target: the reference's own Numba `_loops_deconv`
+    (pybold/bold_signal.py:242-278) on given (h, warm start) against the device recursion fed with the
+    device Frobenius Lipschitz constant -- no theta step involved."""
+    from pybold_b200 import _lib
+    from pybold_b200.bold_signal import deconv_batch
+    g = golden("loops_deconv")
+    for tag in ("a", "b"):                       # the runs without early stopping
+        v, _, lbda, n, es, _ = g["par_" + tag]
+        assert not es
+        y = torch.as_tensor(g["y"][int(v)], device="cuda").reshape(1, -1)
+        h = torch.as_tensor(g["h_" + tag], device="cuda")
+        w0 = torch.as_tensor(g["w0_" + tag], device="cuda").reshape(1, -1).contiguous()
+        L = torch.empty(1, dtype=torch.float64, device="cuda")
+        assert _lib.lib.pb_lipschitz_frob_f64(h.data_ptr(), 0, L.data_ptr(), 1, y.shape[1], h.numel(), 0) == 0
+        x, z, dz, J, n_it = deconv_batch(y, h, float(lbda), L, w0, False, 1e-6, 6, int(n))
+        assert rel(dz[0].cpu().numpy(), g["w_" + tag]) < 1e-9, tag
