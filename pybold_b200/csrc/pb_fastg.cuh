@@ -111,8 +111,14 @@ struct Seg<float, G> {
 // stores its R values as 16-byte vectors into a per-voxel buffer framed by zero pads and loads the
 // preceding / following samples as vectors (R % 4 == 0).  10 + 10 instead of 38 + 38 instructions
 // per convolution pair at K = 20 and no boundary selects; measured +17 % at T = 600 (pb_fastc.cuh).
+#ifdef PB_LEAN_KEEP_TAPS
+constexpr bool kLeanTaps = false;   // experiment: LEAN moves only dy to shared memory
+#else
+constexpr bool kLeanTaps = true;
+#endif
 template <typename real, int R, int KMAX, int G, int TAIL, int J0, bool LEAN = false, bool SMH = false>
 struct GroupVoxel {
+    static constexpr bool LT = LEAN && kLeanTaps;
     static_assert(!SMH || R % 4 == 0, "SMH moves 16-byte vectors");
     static constexpr int NH = (KMAX - 1 + 3) / 4;   // vectors per halo
     struct alignas(4 * sizeof(real)) V4 { real t[4]; };
@@ -123,7 +129,7 @@ struct GroupVoxel {
     static_assert(!LEAN || KMAX % 4 == 0, "LEAN fetches taps as 16-byte vectors");
     real w[R];                     // iterate (the reference's diff_z)
     real dy[LEAN ? 1 : R];         // y[i] - y[i-1]            (registers unless LEAN)
-    real h[LEAN ? 1 : KMAX];       // taps, zero beyond K       (registers unless LEAN)
+    real h[LT ? 1 : KMAX];         // taps, zero beyond K       (registers unless LEAN)
     real *dy_s;                    // LEAN: dy[r] at dy_s[r * 32]  (pointer already offset by lane)
     const real *h_s;               // LEAN: this group's KMAX taps, 16-byte aligned
     int nvalid;                    // samples (< T) this lane holds
@@ -190,7 +196,7 @@ struct GroupVoxel {
     template <int JS>
     __device__ __forceinline__ void conv_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
-        if constexpr (LEAN) {
+        if constexpr (LT) {
 #pragma unroll
             for (int jj = 0; jj < KMAX / 4; ++jj) {
                 const Tap4 t4 = reinterpret_cast<const Tap4 *>(h_s)[jj];
@@ -221,7 +227,7 @@ struct GroupVoxel {
     template <int JS>
     __device__ __forceinline__ void corr_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
-        if constexpr (LEAN) {
+        if constexpr (LT) {
 #pragma unroll
             for (int jj = 0; jj < KMAX / 4; ++jj) {
                 const Tap4 t4 = reinterpret_cast<const Tap4 *>(h_s)[jj];
@@ -311,13 +317,13 @@ struct GroupVoxel {
     }
     // taps of this group's voxel from the double scratch (call with the whole warp converged)
     __device__ __forceinline__ void load_taps(const double *hs, int K) {
-        if constexpr (LEAN) {
+        if constexpr (LT) {
             __syncwarp();
             for (int j = q; j < KMAX; j += G) const_cast<real *>(h_s)[j] = j < K ? (real)hs[j] : real(0);
             __syncwarp();
         } else {
 #pragma unroll
-            for (int j = 0; j < KMAX; ++j) h[LEAN ? 0 : j] = j < K ? (real)hs[j] : real(0);
+            for (int j = 0; j < KMAX; ++j) h[LT ? 0 : j] = j < K ? (real)hs[j] : real(0);
         }
     }
     __device__ __forceinline__ void load_y(const real *yv, int T, real (&y)[R]) const {

@@ -289,3 +289,23 @@ def test_inner_loop_stage_vs_reference_numba_golden(golden):
         assert _lib.lib.pb_lipschitz_frob_f64(h.data_ptr(), 0, L.data_ptr(), 1, y.shape[1], h.numel(), 0) == 0
         x, z, dz, J, n_it = deconv_batch(y, h, float(lbda), L, w0, False, 1e-6, 6, int(n))
         assert rel(dz[0].cpu().numpy(), g["w_" + tag]) < 1e-9, tag
+
+
+def test_deconv_lbda_path_matches_single_lambda_calls():
+    """cfg5-style regularisation path: batched over (lambda, voxel) == one deconv per lambda."""
+    import pybold_b200 as pb
+    from pybold_b200.bold_signal import deconv_lbda_path
+    V, T = 7, 600
+    y = gen_voxels(V, T, 1.0, 20.0, seed0=9000)
+    h, _ = orc.spm_hrf(1.0, 1.0, 20.0, True)
+    x0 = np.random.RandomState(2).randn(T)
+    lbdas = np.geomspace(0.05, 20, 5)
+    x, z, dz, J = deconv_lbda_path(y, 1.0, h, lbdas, nb_iter=40, x0=x0, max_problems=16)
+    assert z.shape == (5, V, T) and J.shape == (5, V, 40)
+    for i in (0, 4):
+        x1, z1, dz1, J1, _, _ = pb.deconv(y, 1.0, h, lbda=float(lbdas[i]), early_stopping=False,
+                                         nb_iter=40, x0=x0)
+        assert np.array_equal(z[i], z1) and np.array_equal(J[i], J1)
+    Lc = 0.9 * orc.spectral_radius_est(orc.HrfIntegOperator(h, T), x0)
+    xo, zo, wo, Jo, _ = orc.deconv_fixed_lbda(y[3], h, lbdas[2], lipschitz=Lc, early_stopping=False, nb_iter=40)
+    assert rel(dz[2, 3], wo) < 1e-9 and rel(J[2, 3], Jo) < 1e-9

@@ -117,11 +117,9 @@ int main(int argc, char **argv) {
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
-        rung<19, 20, 16, 8, 7, 2>("G16 R19 K20 T8 W7 M2", b, 100);
-        rung<19, 20, 16, 8, 13, 1>("G16 R19 K20 T8 W13 M1", b, 100);
-        rung<19, 20, 16, 8, 14, 1>("G16 R19 K20 T8 W14 M1", b, 100);
-        rung<19, 20, 16, 8, 12, 1>("G16 R19 K20 T8 W12 M1", b, 100);
-        rung<19, 20, 16, 8, 6, 2>("G16 R19 K20 T8 W6 M2", b, 100);
+        rung<19, 20, 16, 8, 4, 4, true>("G16 R19 K20 T8 W4 M4 LEAN(dy only)", b, 100);
+        rung<19, 20, 16, 8, 4, 3, true>("G16 R19 K20 T8 W4 M3 LEAN(dy only)", b, 100);
+        rung<19, 20, 16, 8, 8, 2, true>("G16 R19 K20 T8 W8 M2 LEAN(dy only)", b, 100);
         b.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
