@@ -3,7 +3,6 @@ final gather.  The solve itself needs a GPU; here each rank runs a stand-in that
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
