@@ -117,9 +117,6 @@ int main(int argc, char **argv) {
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
-        rung<19, 20, 16, 8, 4, 4, true>("G16 R19 K20 T8 W4 M4 LEAN(dy only)", b, 100);
-        rung<19, 20, 16, 8, 4, 3, true>("G16 R19 K20 T8 W4 M3 LEAN(dy only)", b, 100);
-        rung<19, 20, 16, 8, 8, 2, true>("G16 R19 K20 T8 W8 M2 LEAN(dy only)", b, 100);
         b.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
