@@ -2,11 +2,13 @@
 // Host-side argument checks, shared-memory sizing, persistent-grid sizing and dispatch between
 // the register-tiled warp kernels (pb_fast.cuh) and the generic kernels (pb_generic.cuh).
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 
 #include "../../include/pybold_b200.h"
 #include "pb_fast_registry.h"
 #include "pb_ops.cuh"
+#include "pb_ops_rows.cuh"
 
 #define PB_VERSION 100   /* 0.1.0 */
 #define PB_MAX_T 4096
@@ -86,6 +88,76 @@ pb::HrfGrid make_grid(double t_r, double dur, int *n_fine) {
     return g;
 }
 
+// Register-resident row kernels (pb_ops_rows.cuh) for the shapes they cover; NO_FAST_OP otherwise.
+constexpr int NO_FAST_OP = -1000;
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename real, bool REV, int NCH>
+int launch_rows_scan(const DeviceInfo &d, const real *x, real *out, int64_t V, int T, pb_stream_t stream) {
+    const int64_t need = (V + 7) / 8;
+    const int64_t cap = (int64_t)d.sm_count * 8;
+    pb::rows_scan_kernel<real, REV, NCH><<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        x, out, V, T);
+    return last_error();
+}
+
+template <typename real, bool REV>
+int run_rows_scan(const real *x, real *out, int64_t V, int T, pb_stream_t stream) {
+    constexpr int VEC = pb::Vec16<real>::N;
+    if (T % VEC != 0 || !aligned16(x) || !aligned16(out) || T > 32 * VEC * 10) return NO_FAST_OP;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int nch = (T + 32 * VEC - 1) / (32 * VEC);
+    if (nch <= 3) return launch_rows_scan<real, REV, 3>(d, x, out, V, T, stream);
+    if (nch <= 5) return launch_rows_scan<real, REV, 5>(d, x, out, V, T, stream);
+    return launch_rows_scan<real, REV, 10>(d, x, out, V, T, stream);
+}
+
+template <int OP, int KMAX, int NCH>
+int launch_rows_conv(const DeviceInfo &d, const float *h, int64_t h_stride, const float *x, float *out,
+                     int64_t V, int T, int K, pb_stream_t stream) {
+    using L = pb::RowsConvLayout<float, KMAX, NCH>;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * L::WARP_BYTES;
+    auto kern = pb::rows_conv_kernel<float, OP, KMAX, NCH>;
+    int e = set_smem(kern, smem);
+    if (e) return e;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return NO_FAST_OP;
+    }
+    const int64_t need = (V + warps - 1) / warps;
+    const int64_t cap = (int64_t)d.sm_count * occ;
+    kern<<<(int)(need < cap ? need : cap), warps * 32, smem, (cudaStream_t)stream>>>(h, h_stride, x, out, V, T, K);
+    return last_error();
+}
+
+template <int OP, int KMAX>
+int pick_rows_conv_nch(const DeviceInfo &d, const float *h, int64_t h_stride, const float *x, float *out,
+                       int64_t V, int T, int K, pb_stream_t stream) {
+    const int nch = (T + 127) / 128;
+    if (nch <= 3) return launch_rows_conv<OP, KMAX, 3>(d, h, h_stride, x, out, V, T, K, stream);
+    if (nch <= 5) return launch_rows_conv<OP, KMAX, 5>(d, h, h_stride, x, out, V, T, K, stream);
+    return launch_rows_conv<OP, KMAX, 10>(d, h, h_stride, x, out, V, T, K, stream);
+}
+
+template <int OP>
+int run_rows_conv(const float *h, int64_t h_stride, const float *x, float *out, int64_t V, int T, int K,
+                  pb_stream_t stream) {
+    if (T % 4 != 0 || !aligned16(x) || !aligned16(out) || T > 1280 || K > 32) return NO_FAST_OP;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    if (K <= 20) return pick_rows_conv_nch<OP, 20>(d, h, h_stride, x, out, V, T, K, stream);
+    if (K <= 28) return pick_rows_conv_nch<OP, 28>(d, h, h_stride, x, out, V, T, K, stream);
+    return pick_rows_conv_nch<OP, 32>(d, h, h_stride, x, out, V, T, K, stream);
+}
+template <int OP>
+int run_rows_conv(const double *, int64_t, const double *, double *, int64_t, int, int, pb_stream_t) {
+    return NO_FAST_OP;      // the double build uses op_kernel
+}
+
 template <typename real, int OP>
 int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V, int T, int K,
            pb_stream_t stream) {
@@ -93,7 +165,13 @@ int run_op(const real *h, int64_t h_stride, const real *x, real *out, int64_t V,
     if (!x || !out || V < 0 || T <= 0) return PB_ERR_INVALID_ARG;
     if (OP >= pb::OP_CONV && (!h || K <= 0)) return PB_ERR_INVALID_ARG;
     if (T > PB_MAX_T || K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
-    if (V == 0) return PB_OK;
+    {
+        int rc = NO_FAST_OP;
+        if constexpr (OP == pb::OP_INTEG) rc = run_rows_scan<real, false>(x, out, V, T, stream);
+        else if constexpr (OP == pb::OP_INTEG_ADJ) rc = run_rows_scan<real, true>(x, out, V, T, stream);
+        else rc = run_rows_conv<OP>(h, h_stride, x, out, V, T, K, stream);
+        if (rc != NO_FAST_OP) return rc;
+    }
     DeviceInfo d = device_info();
     if (d.err) return d.err;
     pb::OpLayout lay = pb::OpLayout::make(T, OP >= pb::OP_CONV ? K : 1);

@@ -137,3 +137,57 @@ def test_layout_adapter_roundtrip_and_ragged_tiles():
         assert np.array_equal(back.cpu().numpy(), a)
     with pytest.raises(ValueError):
         voxels_from_timeseries(np.zeros(5))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_row_kernels_all_shapes(dt):
+    """Register-resident row kernels (pb_ops_rows.cuh) and the generic fallback against NumPy float64:
+    16-byte aligned rows (fast path), ragged rows and long kernels (fallback), shared and per-row
+    taps, chunks partly or wholly beyond the row end."""
+    import pybold_b200 as pb
+    from pybold_b200 import convolution as cv
+    rng = np.random.RandomState(11)
+    tol = 3e-5 if dt is np.float32 else 1e-12
+    shapes = [(9, 4, 1), (33, 128, 5), (70, 300, 20), (40, 384, 20), (21, 388, 28), (19, 600, 32),
+              (13, 640, 28), (11, 1200, 28), (7, 1280, 20), (5, 1284, 20), (6, 301, 20), (4, 600, 40),
+              (3, 2, 3)]
+    for (V, T, K) in shapes:
+        xn = rng.randn(V, T)
+        for per_row in (False, True):
+            kn = rng.randn(V, K) if per_row else rng.randn(K)
+            x = torch.as_tensor(xn.astype(dt), device="cuda")
+            k = torch.as_tensor(kn.astype(dt), device="cuda")
+            x64 = x.cpu().numpy().astype(np.float64)
+            k64 = np.broadcast_to(k.cpu().numpy().astype(np.float64), (V, K))
+            conv = np.stack([orc.conv_causal(k64[v], x64[v]) for v in range(V)])
+            corr = np.stack([np.correlate(np.concatenate([x64[v], np.zeros(K - 1)]), k64[v], "valid")
+                             for v in range(V)])
+            cs = np.cumsum(x64, axis=1)
+            rcs = np.cumsum(x64[:, ::-1], axis=1)[:, ::-1]
+            D = pb.DiscretInteg()
+            H = pb.ConvAndLinear(D, k, dim_in=T)
+            hop = np.stack([orc.conv_causal(k64[v], cs[v]) for v in range(V)])
+            hadj = np.cumsum(corr[:, ::-1], axis=1)[:, ::-1]
+            got = {"conv": cv.simple_convolve(k, x), "corr": cv.simple_retro_convolve(k, x),
+                   "integ": D.op(x), "integ_adj": D.adj(x), "H.op": H.op(x), "H.adj": H.adj(x)}
+            want = {"conv": conv, "corr": corr, "integ": cs, "integ_adj": rcs, "H.op": hop, "H.adj": hadj}
+            for name in got:
+                assert got[name].shape == (V, T)
+                assert rel(got[name].cpu().numpy(), want[name]) < tol, (name, V, T, K, per_row, dt)
+
+
+def test_row_kernels_in_place_and_misaligned():
+    """The C ABI allows out == x; rows that do not start on 16-byte boundaries take the fallback."""
+    from pybold_b200 import _lib
+    rng = np.random.RandomState(12)
+    V, T = 37, 300
+    xn = rng.randn(V, T).astype(np.float32)
+    want = np.cumsum(xn.astype(np.float64), axis=1)
+    x = torch.as_tensor(xn, device="cuda")
+    assert _lib.lib.pb_integ_op_f32(x.data_ptr(), x.data_ptr(), V, T, 0) == 0
+    assert rel(x.cpu().numpy(), want) < 3e-5
+    buf = torch.zeros(V * T + 1, device="cuda", dtype=torch.float32)
+    buf[1:] = torch.as_tensor(xn, device="cuda").reshape(-1)
+    out = torch.empty(V * T + 1, device="cuda", dtype=torch.float32)
+    assert _lib.lib.pb_integ_op_f32(buf.data_ptr() + 4, out.data_ptr() + 4, V, T, 0) == 0
+    assert rel(out[1:].reshape(V, T).cpu().numpy(), want) < 3e-5
