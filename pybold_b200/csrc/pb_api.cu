@@ -249,7 +249,7 @@ template <typename real>
 int run_transpose(const real *in, real *out, int64_t rows, int64_t cols, pb_stream_t stream) {
     if (rows == 0 || cols == 0) return PB_OK;
     if (!in || !out || rows < 0 || cols < 0 || in == out) return PB_ERR_INVALID_ARG;
-    const int64_t gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+    const int64_t gx = (cols + 63) / 64, gy = (rows + 63) / 64;
     if (gy > 65535 || gx > 2147483647LL) return PB_ERR_UNSUPPORTED;
     pb::transpose_kernel<real><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(
         in, out, rows, cols);

@@ -241,21 +241,32 @@ __global__ void lipschitz_frob_kernel(const real *h, int64_t h_stride, real *out
 // consumed as `voxels.T`); the solvers want [V, T].  32 x 32 tiles through padded shared memory:
 // coalesced 128-byte rows on both sides, HBM bound (2 x 4 bytes per sample).
 template <typename real>
-__global__ void transpose_kernel(const real *in, real *out, int64_t rows, int64_t cols) {
-    __shared__ real tile[32][33];
-    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+__global__ void __launch_bounds__(256) transpose_kernel(const real *__restrict__ in, real *out, int64_t rows,
+                                                         int64_t cols) {
+    // 64 x 64 tiles: 256-byte runs on both sides and 16 independent loads per thread in flight
+    __shared__ real tile[64][65];
+    const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
     const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8 threads
+    real v[16];
 #pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-        const int64_t r = r0 + ty + k, c = c0 + tx;
-        if (r < rows && c < cols) tile[ty + k][tx] = in[r * cols + c];
-    }
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int64_t r = r0 + ty + 8 * k, c = c0 + tx + 32 * hf;
+            v[2 * k + hf] = (r < rows && c < cols) ? in[r * cols + c] : real(0);
+        }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) tile[ty + 8 * k][tx + 32 * hf] = v[2 * k + hf];
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 32; k += 8) {
-        const int64_t c = c0 + ty + k, r = r0 + tx;
-        if (r < rows && c < cols) out[c * rows + r] = tile[tx][ty + k];
-    }
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int64_t c = c0 + ty + 8 * k, r = r0 + tx + 32 * hf;
+            if (r < rows && c < cols) out[c * rows + r] = tile[tx + 32 * hf][ty + 8 * k];
+        }
 }
 
 // hrf_estim / the theta step alone (pybold/bold_signal.py:217-239, :329-334)

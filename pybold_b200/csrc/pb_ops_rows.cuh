@@ -106,6 +106,11 @@ rows_scan_kernel(const real *__restrict__ x, real *out, int64_t V, int T) {
 // K-tap causal convolution / anti-causal correlation of the rows, optionally fused with the
 // integration operator: OP_CONV, OP_CONV_ADJ, OP_HRFINTEG (conv o cumsum), OP_HRFINTEG_ADJ
 // (reversed cumsum o corr).
+//
+// Bound by shared-memory bandwidth, not HBM (ncu, K = 28: 70 % of the shared-memory wavefront peak,
+// l1tex 87 %, at 0.71 of the HBM copy rate): every sample is read by (K + 6) / 4 lanes.  Measured
+// and rejected: two adjacent output vectors per lane (half the window loads, but 32-byte lane
+// strides double the wavefronts per load: 0.65); three CTAs per SM (spills, no gain).
 template <int KMAX, int VEC>
 __host__ __device__ constexpr int rows_conv_nc() { return (KMAX - 1 + VEC - 1) / VEC + 1; }
 
