@@ -164,6 +164,29 @@ int pb_hrf_estim_f64(const double *z, const double *y, double t_r, double hrf_du
                      double *out_theta, double *out_h, double *out_cost,
                      int64_t V, int T, int K, pb_stream_t stream);
 
+/* ---- N3: on-device synthetic voxels and the post-processing of the ICASSP-2019 simulation.
+ * pb_synth_voxels: the batch that `examples/icassp_2019/simulation.py:27-48` builds one voxel at a time
+ * with `gen_rnd_bloc_bold` (pybold/data.py:243-400): `nb_events` unit boxcars of `blk` samples, the
+ * normalised SPM HRF at a per-voxel dilation in [delta_lo, delta_hi], Gaussian noise at `snr_db`
+ * (scaling rule of pybold/data.py:439-444).  Own counter-based generator ("philox-v1", csrc/pb_synth.cuh;
+ * NumPy restatement in pybold_b200/synth.py): voxel `first_voxel + v` gets the same numbers on every
+ * rank and for every batch split.  out_z (block signal) and out_delta may be null.  nb_events <= 31.
+ * pb_inf_norm: out[v,:] = x[v,:] / (max|x[v,:]| + 1e-12)  (pybold/utils.py:112-138, 2-D input, axis=1).
+ * pb_rel_l2_err: err[v] = ||est[v,:] - ref[v,:]|| / ||ref[v,:]||  (simulation.py:143-147); ref_stride = 0
+ * compares every voxel with one reference row. */
+int pb_synth_voxels_f32(uint64_t seed, int64_t first_voxel, double t_r, double hrf_dur, double snr_db,
+                        int nb_events, int blk, double delta_lo, double delta_hi, float *out_y,
+                        float *out_z, float *out_delta, int64_t V, int T, pb_stream_t stream);
+int pb_synth_voxels_f64(uint64_t seed, int64_t first_voxel, double t_r, double hrf_dur, double snr_db,
+                        int nb_events, int blk, double delta_lo, double delta_hi, double *out_y,
+                        double *out_z, double *out_delta, int64_t V, int T, pb_stream_t stream);
+int pb_inf_norm_f32(const float *x, float *out, int64_t V, int T, pb_stream_t stream);
+int pb_inf_norm_f64(const double *x, double *out, int64_t V, int T, pb_stream_t stream);
+int pb_rel_l2_err_f32(const float *est, const float *ref, int64_t ref_stride, float *out_err,
+                      int64_t V, int T, pb_stream_t stream);
+int pb_rel_l2_err_f64(const double *est, const double *ref, int64_t ref_stride, double *out_err,
+                      int64_t V, int T, pb_stream_t stream);
+
 /* ---- N4: layout adapter between the reference pipeline's time-major voxel matrices [T, V]
  * (`NiftiMasker.fit_transform`, consumed as `voxels.T`, examples/icassp_2019/validation.py:90-103)
  * and the solvers' [V, T]: out[c, r] = in[r, c] for an in[rows, cols] row-major matrix.  Out of place

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpybold_b200.so")
@@ -54,6 +54,10 @@ _OPS = {
               c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
               c_int64, c_int, c_int, _P],
     "pb_transpose": [_P, _P, c_int64, c_int64, _P],
+    "pb_synth_voxels": [c_uint64, c_int64, c_double, c_double, c_double, c_int, c_int, c_double, c_double,
+                        _P, _P, _P, c_int64, c_int, _P],
+    "pb_inf_norm": [_P, _P, c_int64, c_int, _P],
+    "pb_rel_l2_err": [_P, _P, c_int64, _P, c_int64, c_int, _P],
     "pb_hrf_estim": [_P, _P, c_double, c_double, _P, c_int64, c_double, c_double, _P, _P, _P,
                      c_int64, c_int, c_int, _P],
 }

@@ -9,6 +9,7 @@
 #include "pb_fast_registry.h"
 #include "pb_ops.cuh"
 #include "pb_ops_rows.cuh"
+#include "pb_synth.cuh"
 
 #define PB_VERSION 100   /* 0.1.0 */
 #define PB_MAX_T 4096
@@ -332,6 +333,58 @@ int run_hrf_estim(const real *z, const real *y, double t_r, double hrf_dur, cons
     return last_error();
 }
 
+template <typename real>
+int run_synth(uint64_t seed, int64_t first_voxel, double t_r, double hrf_dur, double snr_db, int nb_events,
+              int blk, double delta_lo, double delta_hi, real *out_y, real *out_z, real *out_delta, int64_t V,
+              int T, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!out_y || V < 0 || T <= 0 || first_voxel < 0 || nb_events < 0 || blk < 1 || !(t_r >= 0.001) ||
+        !(hrf_dur > 0.002) || !(delta_lo <= delta_hi) || !(delta_lo >= 0.5) || !(delta_hi <= 2.0))
+        return PB_ERR_INVALID_ARG;
+    if (T > PB_MAX_T || nb_events > pb::PB_SYNTH_MAX_EVENTS) return PB_ERR_UNSUPPORTED;
+    pb::SynthArgs a;
+    a.seed = seed; a.first_voxel = first_voxel; a.grid = make_grid(t_r, hrf_dur, nullptr);
+    a.delta_lo = delta_lo; a.delta_hi = delta_hi; a.snr_db = snr_db; a.nb_events = nb_events; a.blk = blk;
+    a.V = V; a.T = T;
+    if (a.grid.K < 1 || a.grid.K > PB_MAX_OP_K) return PB_ERR_UNSUPPORTED;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int warps = 4;
+    const size_t smem = (size_t)warps * ((((size_t)T * sizeof(float) + 15) & ~(size_t)15) +
+                                         (size_t)a.grid.K * sizeof(double));
+    auto kern = pb::synth_voxels_kernel<real>;
+    int e = set_smem(kern, smem);
+    if (e) return e;
+    const int64_t need = (V + warps - 1) / warps;
+    const int64_t cap = (int64_t)d.sm_count * 8;
+    kern<<<(int)(need < cap ? need : cap), warps * 32, smem, (cudaStream_t)stream>>>(a, out_y, out_z, out_delta);
+    return last_error();
+}
+
+template <typename real>
+int run_inf_norm(const real *x, real *out, int64_t V, int T, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!x || !out || V < 0 || T <= 0) return PB_ERR_INVALID_ARG;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int64_t need = (V + 7) / 8, cap = (int64_t)d.sm_count * 8;
+    pb::inf_norm_kernel<real><<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(x, out, V, T);
+    return last_error();
+}
+
+template <typename real>
+int run_rel_l2_err(const real *est, const real *ref, int64_t ref_stride, real *out_err, int64_t V, int T,
+                   pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!est || !ref || !out_err || V < 0 || T <= 0 || ref_stride < 0) return PB_ERR_INVALID_ARG;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int64_t need = (V + 7) / 8, cap = (int64_t)d.sm_count * 8;
+    pb::rel_l2_err_kernel<real><<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        est, ref, ref_stride, out_err, V, T);
+    return last_error();
+}
+
 __global__ void fma_peak_kernel(float *sink, int iters) {
     float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -447,6 +500,20 @@ int pb_hrf_len(double t_r, double dur) {
     }                                                                                                  \
     int pb_transpose_##SUF(const REAL *in, REAL *out, int64_t rows, int64_t cols, pb_stream_t s) {    \
         return run_transpose<REAL>(in, out, rows, cols, s);                                            \
+    }                                                                                                  \
+    int pb_synth_voxels_##SUF(uint64_t seed, int64_t first_voxel, double t_r, double hrf_dur,         \
+                              double snr_db, int nb_events, int blk, double delta_lo, double delta_hi, \
+                              REAL *out_y, REAL *out_z, REAL *out_delta, int64_t V, int T,             \
+                              pb_stream_t s) {                                                         \
+        return run_synth<REAL>(seed, first_voxel, t_r, hrf_dur, snr_db, nb_events, blk, delta_lo,      \
+                               delta_hi, out_y, out_z, out_delta, V, T, s);                            \
+    }                                                                                                  \
+    int pb_inf_norm_##SUF(const REAL *x, REAL *out, int64_t V, int T, pb_stream_t s) {                 \
+        return run_inf_norm<REAL>(x, out, V, T, s);                                                    \
+    }                                                                                                  \
+    int pb_rel_l2_err_##SUF(const REAL *est, const REAL *ref, int64_t ref_stride, REAL *out_err,       \
+                            int64_t V, int T, pb_stream_t s) {                                         \
+        return run_rel_l2_err<REAL>(est, ref, ref_stride, out_err, V, T, s);                           \
     }                                                                                                  \
     int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
                            const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \

@@ -37,3 +37,48 @@ def spectral_radius_est(L, x_shape, nb_iter=30, tol=1.0e-6, verbose=False, x0=No
     if scalar:
         return float(out[0])
     return out if isinstance(x0, torch.Tensor) else out.cpu().numpy()
+
+
+def _rows(name, x, *extra):
+    dtype = pick_dtype(x)
+    xd = to_device(x, dtype)
+    one_d = xd.dim() == 1
+    x2 = (xd.reshape(1, -1) if one_d else xd).contiguous()
+    return dtype, xd, one_d, x2
+
+
+def inf_norm(arrays, axis=1):
+    """Inf-norm normalisation ``x / (max|x| + 1e-12)`` (pybold/utils.py:112-138): 1-D arrays as a whole,
+    2-D arrays row by row (``axis=1``; ``axis=0`` normalises the columns), lists element-wise."""
+    from ._array import like_input
+    if isinstance(arrays, list):
+        return [inf_norm(a, axis=axis) for a in arrays]
+    dtype, xd, one_d, x2 = _rows("pb_inf_norm", arrays)
+    if xd.dim() > 2:
+        raise ValueError("inf-norm normalization only handle 1D or 2D arrays on the device")
+    if not one_d and axis == 0:
+        x2 = x2.t().contiguous()
+    out = torch.empty_like(x2)
+    rc = _lib.fn("pb_inf_norm", dtype)(ptr(x2), ptr(out), x2.shape[0], x2.shape[1], stream_ptr())
+    _lib.check(rc, "pb_inf_norm")
+    if not one_d and axis == 0:
+        out = out.t().contiguous()
+    return like_input(out.reshape(-1) if one_d else out, arrays)
+
+
+def rel_l2_err(est, ref):
+    """Per-voxel relative L2 error ``||est_v - ref_v|| / ||ref_v||`` of the ICASSP-2019 simulation
+    (examples/icassp_2019/simulation.py:143-147); ``ref`` is ``[V, T]`` or one shared row ``[T]``."""
+    from ._array import like_input
+    dtype = pick_dtype(est, ref)
+    e2 = to_device(est, dtype)
+    r2 = to_device(ref, dtype).contiguous()
+    e2 = (e2.reshape(1, -1) if e2.dim() == 1 else e2).contiguous()
+    V, T = e2.shape
+    if r2.shape[-1] != T or (r2.dim() == 2 and r2.shape[0] not in (1, V)):
+        raise ValueError("rel_l2_err: est %s and ref %s do not match" % (tuple(e2.shape), tuple(r2.shape)))
+    stride = T if (r2.dim() == 2 and r2.shape[0] == V and V > 1) else 0
+    out = torch.empty(V, dtype=dtype, device=e2.device)
+    rc = _lib.fn("pb_rel_l2_err", dtype)(ptr(e2), ptr(r2), stride, ptr(out), V, T, stream_ptr())
+    _lib.check(rc, "pb_rel_l2_err")
+    return like_input(out, est)
