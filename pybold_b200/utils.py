@@ -1,4 +1,5 @@
-"""Hot-path subset of ``pybold/utils.py``: the power-iteration Lipschitz estimate."""
+"""Hot-path subset of ``pybold/utils.py``: the power-iteration Lipschitz estimate, ``inf_norm`` and the
+relative-error metric of the ICASSP-2019 simulation (row N3)."""
 from __future__ import annotations
 
 import numpy as np
@@ -39,7 +40,7 @@ def spectral_radius_est(L, x_shape, nb_iter=30, tol=1.0e-6, verbose=False, x0=No
     return out if isinstance(x0, torch.Tensor) else out.cpu().numpy()
 
 
-def _rows(name, x, *extra):
+def _rows(x):
     dtype = pick_dtype(x)
     xd = to_device(x, dtype)
     one_d = xd.dim() == 1
@@ -53,7 +54,7 @@ def inf_norm(arrays, axis=1):
     from ._array import like_input
     if isinstance(arrays, list):
         return [inf_norm(a, axis=axis) for a in arrays]
-    dtype, xd, one_d, x2 = _rows("pb_inf_norm", arrays)
+    dtype, xd, one_d, x2 = _rows(arrays)
     if xd.dim() > 2:
         raise ValueError("inf-norm normalization only handle 1D or 2D arrays on the device")
     if not one_d and axis == 0:
