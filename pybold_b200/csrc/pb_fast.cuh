@@ -26,6 +26,35 @@
 #include "pb_fast_registry.h"
 #include "pb_generic.cuh"
 
+#include "pb_tile.cuh"
+
+// source order of the unrolled tile (pb_tile.cuh), picked with the register-file model on
+// fast_deconv_kernel<float, 20, 20, circ> (cfg5: 1918 -> 1831 modelled cycles per iteration)
+#ifndef PB_W_CONV_JDESC
+#define PB_W_CONV_JDESC 1
+#endif
+#ifndef PB_W_CONV_RDESC
+#define PB_W_CONV_RDESC 0
+#endif
+#ifndef PB_W_CONV_RB
+#define PB_W_CONV_RB 10
+#endif
+#ifndef PB_W_CONV_DS
+#define PB_W_CONV_DS 0
+#endif
+#ifndef PB_W_CORR_JDESC
+#define PB_W_CORR_JDESC 1
+#endif
+#ifndef PB_W_CORR_RDESC
+#define PB_W_CORR_RDESC 1
+#endif
+#ifndef PB_W_CORR_RB
+#define PB_W_CORR_RB 10
+#endif
+#ifndef PB_W_CORR_DS
+#define PB_W_CORR_DS 0
+#endif
+
 namespace pb {
 
 template <int R, int KMAX>
@@ -86,28 +115,12 @@ struct WarpVoxel {
     // acc[r] += sum_j h[j] a(i - j)
     __device__ __forceinline__ void conv_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r - j;
-                const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
-                acc[r] = fma(h[j], val, acc[r]);
-            }
-        }
+        tile_conv<real, R, KMAX, KMAX - 1, 0, PB_W_CONV_JDESC, PB_W_CONV_RDESC, PB_W_CONV_RB, PB_W_CONV_DS>(h, a, halo, acc);
     }
     // acc[r] += sum_j h[j] a(i + j)
     __device__ __forceinline__ void corr_acc(const real (&a)[R], const real (&halo)[KMAX - 1],
                                              real (&acc)[R]) const {
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r + j;
-                const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
-                acc[r] = fma(h[j], val, acc[r]);
-            }
-        }
+        tile_corr<real, R, KMAX, KMAX - 1, 0, PB_W_CORR_JDESC, PB_W_CORR_RDESC, PB_W_CORR_RB, PB_W_CORR_DS>(h, a, halo, acc);
     }
     // in-place inclusive prefix sum over the whole voxel
     __device__ __forceinline__ void scan_fwd(real (&a)[R]) const {

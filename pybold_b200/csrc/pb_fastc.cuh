@@ -22,6 +22,35 @@
 #include "pb_fast_registry.h"
 #include "pb_generic.cuh"
 
+#include "pb_tile.cuh"
+
+// source order of the unrolled tile (pb_tile.cuh), picked with the register-file model on
+// fast_bdc_kernel<float, 20, 28, 2, 6> (cfg4: 1587 -> 1457 modelled cycles per inner iteration)
+#ifndef PB_C_CONV_JDESC
+#define PB_C_CONV_JDESC 1
+#endif
+#ifndef PB_C_CONV_RDESC
+#define PB_C_CONV_RDESC 0
+#endif
+#ifndef PB_C_CONV_RB
+#define PB_C_CONV_RB 8
+#endif
+#ifndef PB_C_CONV_DS
+#define PB_C_CONV_DS 0
+#endif
+#ifndef PB_C_CORR_JDESC
+#define PB_C_CORR_JDESC 1
+#endif
+#ifndef PB_C_CORR_RDESC
+#define PB_C_CORR_RDESC 1
+#endif
+#ifndef PB_C_CORR_RB
+#define PB_C_CORR_RB 5
+#endif
+#ifndef PB_C_CORR_DS
+#define PB_C_CORR_DS 0
+#endif
+
 namespace pb {
 
 template <typename real, int R, int KMAX, int NW>
@@ -103,26 +132,10 @@ fast_bdc_kernel(BdArgs<real> p) {
         }
     };
     auto conv_acc = [&](const real (&a)[R], const real (&hal)[4 * NH], real (&acc)[R]) {
-#pragma unroll
-        for (int j = 1; j < KMAX; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r - j;
-                const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : hal[idx >= 0 ? 0 : -idx - 1];
-                acc[r] = fma(h[j], val, acc[r]);
-            }
-        }
+        tile_conv<real, R, KMAX, 4 * NH, 1, PB_C_CONV_JDESC, PB_C_CONV_RDESC, PB_C_CONV_RB, PB_C_CONV_DS>(h, a, hal, acc);
     };
     auto corr_acc = [&](const real (&a)[R], const real (&hal)[4 * NH], real (&acc)[R]) {
-#pragma unroll
-        for (int j = 1; j < KMAX; ++j) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int idx = r + j;
-                const real val = idx < R ? a[idx < R ? idx : 0] : hal[idx < R ? 0 : idx - R];
-                acc[r] = fma(h[j], val, acc[r]);
-            }
-        }
+        tile_corr<real, R, KMAX, 4 * NH, 1, PB_C_CORR_JDESC, PB_C_CORR_RDESC, PB_C_CORR_RB, PB_C_CORR_DS>(h, a, hal, acc);
     };
     auto mask_tail = [&](real (&a)[R]) {
 #pragma unroll

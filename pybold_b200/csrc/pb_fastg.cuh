@@ -24,6 +24,7 @@
 #include "pb_fast_registry.h"
 #include "pb_generic.cuh"
 #include "pb_theta_group.cuh"
+#include "pb_tile.cuh"
 
 namespace pb {
 
@@ -51,8 +52,8 @@ __device__ __forceinline__ float seg_scan_step_down(float inc, int d, int c) {
     return out;
 }
 
-// source order of the unrolled tap / sample loops (ptxas schedules the tile differently for each;
-// picked with the register-file model of profiles/r01_rf_bandwidth.txt and timed on a B200)
+// source order of the unrolled tile (pb_tile.cuh), picked with the register-file model of
+// profiles/r01_rf_bandwidth.txt on fast_bdg_kernel<float, 19, 20, 16, 8, 4, 3> and timed on a B200
 #ifndef PB_CONV_JDESC
 #define PB_CONV_JDESC 1
 #endif
@@ -240,36 +241,7 @@ struct GroupVoxel {
                 }
             }
         } else {
-#if PB_CONV_DS
-            // data-stationary: window position i = -(KMAX-1) .. R-1 (halo first), all taps of it
-#pragma unroll
-            for (int ii = -(KMAX - 1); ii < R; ++ii) {
-                const int i = PB_CONV_DS == 2 ? (R - 1) - (ii + KMAX - 1) : ii;
-                const real val = i >= 0 ? a[i >= 0 ? i : 0] : halo[i >= 0 ? 0 : -i - 1];
-#pragma unroll
-                for (int jj = JS; jj < KMAX; ++jj) {
-                    const int j = PB_CONV_JDESC ? KMAX - 1 + JS - jj : jj;
-                    const int r = i + j;
-                    if (r >= 0 && r < R) acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
-                }
-            }
-#else
-            constexpr int RB = PB_CONV_RB > 0 ? PB_CONV_RB : R;
-#pragma unroll
-            for (int rb = 0; rb < R; rb += RB) {
-#pragma unroll
-                for (int jj = JS; jj < KMAX; ++jj) {
-                    const int j = PB_CONV_JDESC ? KMAX - 1 + JS - jj : jj;
-#pragma unroll
-                    for (int rr = rb; rr < (rb + RB < R ? rb + RB : R); ++rr) {
-                        const int r = PB_CONV_RDESC ? R - 1 - rr : rr;
-                        const int idx = r - j;
-                        const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
-                        acc[r] = fma(h[j], val, acc[r]);
-                    }
-                }
-            }
-#endif
+            tile_conv<real, R, KMAX, KMAX - 1, JS, PB_CONV_JDESC, PB_CONV_RDESC, PB_CONV_RB, PB_CONV_DS>(h, a, halo, acc);
         }
     }
     template <int JS>
@@ -292,36 +264,7 @@ struct GroupVoxel {
                 }
             }
         } else {
-#if PB_CORR_DS
-            // data-stationary: window position i = 0 .. R+KMAX-2 (own samples, then the halo)
-#pragma unroll
-            for (int ii = 0; ii < R + KMAX - 1; ++ii) {
-                const int i = PB_CORR_DS == 2 ? (R + KMAX - 2) - ii : ii;
-                const real val = i < R ? a[i < R ? i : 0] : halo[i < R ? 0 : i - R];
-#pragma unroll
-                for (int jj = JS; jj < KMAX; ++jj) {
-                    const int j = PB_CORR_JDESC ? KMAX - 1 + JS - jj : jj;
-                    const int r = i - j;
-                    if (r >= 0 && r < R) acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
-                }
-            }
-#else
-            constexpr int RB = PB_CORR_RB > 0 ? PB_CORR_RB : R;
-#pragma unroll
-            for (int rb = 0; rb < R; rb += RB) {
-#pragma unroll
-                for (int jj = JS; jj < KMAX; ++jj) {
-                    const int j = PB_CORR_JDESC ? KMAX - 1 + JS - jj : jj;
-#pragma unroll
-                    for (int rr = rb; rr < (rb + RB < R ? rb + RB : R); ++rr) {
-                        const int r = PB_CORR_RDESC ? R - 1 - rr : rr;
-                        const int idx = r + j;
-                        const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
-                        acc[r] = fma(h[j], val, acc[r]);
-                    }
-                }
-            }
-#endif
+            tile_corr<real, R, KMAX, KMAX - 1, JS, PB_CORR_JDESC, PB_CORR_RDESC, PB_CORR_RB, PB_CORR_DS>(h, a, halo, acc);
         }
     }
     __device__ __forceinline__ void scan_fwd(real (&a)[R]) const {
