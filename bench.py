@@ -45,9 +45,9 @@ def algorithmic_flops_per_voxel(T, K, n):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the solver kernel, from the committed
-# `ncu --set full` capture of this very command (profiles/r01_ncu_bd_t300_final.txt); only valid for
+# `ncu --set full` capture of this very command (profiles/r01_ncu_bd_t300_reordered.txt); only valid for
 # the default workload, null otherwise.
-NCU_TRAFFIC_BYTES = {(100000, 300, 100): 738.4e6}
+NCU_TRAFFIC_BYTES = {(100000, 300, 100): 628.3e6}
 
 
 def algorithmic_bytes_per_voxel(T, K, n):
@@ -327,7 +327,7 @@ def main():
         roofline = {
             "bound": "fp32", "achieved": achieved, "peak": fma_tflops, "unit": "TFLOP/s",
             "frac": achieved / fma_tflops, "traffic": NCU_TRAFFIC_BYTES.get((V, T, n)),
-            "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_bd_t300_final.txt); "
+            "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_bd_t300_reordered.txt); "
                             "algorithmic %.1f MB" % (hbm_bytes / 1e6),
             "peak_source": "FFMA microbenchmark in this run (pb_bench_fma_f32); nominal "
                            "%d SMs x 128 lanes x 2 x %.0f MHz = %.1f" % (sms, sm_max, nominal),
