@@ -54,19 +54,24 @@ static const FastEntry<real> *pick(int T, int K) {
     return best;
 }
 
+// cheapest matching group / CTA variant: slots per voxel (lanes x samples per lane) x unrolled taps,
+// ties broken by the tail-select count
 template <typename real>
 static const FastGEntry<real> *pick_group(int T, int K) {
-    int n = 0;
-    const FastGEntry<real> *t = fastc_table<real>(&n);
     const FastGEntry<real> *best = nullptr;
-    for (int i = 0; i < n; ++i)
-        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL < best->R * best->KMAX * best->G * 64 + best->TAIL))
-            best = &t[i];
-    if (best) return best;
-    t = fastg_table<real>(&n);
-    for (int i = 0; i < n; ++i)
-        if (t[i].ok(T, K) && (!best || t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL < best->R * best->KMAX * best->G * 64 + best->TAIL))
-            best = &t[i];
+    long best_cost = 0;
+    for (int which = 0; which < 2; ++which) {
+        int n = 0;
+        const FastGEntry<real> *t = which == 0 ? fastc_table<real>(&n) : fastg_table<real>(&n);
+        for (int i = 0; i < n; ++i) {
+            if (!t[i].ok(T, K)) continue;
+            const long cost = (long)t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL;
+            if (!best || cost < best_cost) {
+                best = &t[i];
+                best_cost = cost;
+            }
+        }
+    }
     return best;
 }
 

@@ -403,8 +403,9 @@ fast_bdc_kernel(BdArgs<real> p) {
 
 template <int R, int KMAX, int NW>
 bool fastc_shape_ok(int T, int K) {
-    // at most R idle slots per warp-pair tail: the last used thread may be partial, threads beyond it idle
-    return K <= KMAX && T <= NW * 32 * R && T > (NW * 32 - 8) * R - R && T >= 1;
+    // the last used thread may be partial, threads beyond it idle; up to half of the threads may idle
+    // (the dispatcher picks the variant with the fewest slots among those that match)
+    return K <= KMAX && T <= NW * 32 * R && T > NW * 16 * R - R && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int NW, int MINB>
