@@ -676,7 +676,8 @@ int fast_deconvg_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
 
 template <int R, int KMAX, int G, int TAIL>
 bool fastg_shape_ok(int T, int K) {
-    return K <= KMAX && T <= G * R && G * R - T <= TAIL && T >= 1;
+    // G = 8 (four short series per warp, TAIL = R: every slot maskable) serves T down to half its slots
+    return K <= KMAX && T <= G * R && (G == 8 && TAIL == R ? 2 * T > G * R : G * R - T <= TAIL) && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
