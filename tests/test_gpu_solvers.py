@@ -211,6 +211,22 @@ def test_bd_generic_kernel_matches_fast_kernel():
     assert rel(z[1], zo) < 1e-8 and rel(h[1], ho) < 1e-8 and rel(d["J"][1], do["J"]) < 1e-9
 
 
+def test_bd_long_series_four_warp_variant_vs_generic_fp64():
+    """1280 < T <= 2560 runs on four warps per voxel in FP32; the FP64 build has no register-tiled
+    variant there (generic shared-memory kernel): two independent implementations, 1e-4."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    for T, t_r in ((2000, 0.72), (1300, 1.0), (2560, 1.0)):
+        K = pb.hrf_model.hrf_len(t_r, 20.0)
+        assert _lib.lib.pb_solver_variant(T, K, 0) // 1000000 == 128 and _lib.lib.pb_solver_variant(T, K, 1) == 0
+        y = gen_voxels(3, T, t_r, 20.0, seed0=7000 + T)
+        x, z, dz, h, d = pb.bd(y, t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0, nb_iter=8)
+        x32, z32, dz32, h32, d32 = pb.bd(y.astype(np.float32), t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0,
+                                         nb_iter=8)
+        assert rel(z32, z) < 1e-4 and rel(x32, x) < 1e-4 and rel(h32, h) < 1e-4
+        assert rel(d32["J"], d["J"]) < 1e-4 and np.max(np.abs(d32["theta"] - d["theta"])) < 1e-4
+
+
 def test_bd_streamed_host_batch_equals_single_launch():
     """Host batches above the streaming threshold are solved chunk by chunk with overlapped copies;
     the result must be bit-identical to the single-launch path, including per-voxel parameters

@@ -7,7 +7,7 @@ from pybold_b200.bold_signal import bd_alloc, bd_batch
 from pybold_b200.hrf_model import hrf_len
 from pybold_b200.synth import gen_voxels_device
 for T, t_r, V in [(100, 1.0, 80000), (128, 0.72, 60000), (150, 1.0, 60000), (190, 1.0, 50000), (350, 1.0, 40000), (330, 0.72, 40000), (405, 1.0, 30000), (500, 0.72, 24000), (650, 1.0, 20000),
-                  (700, 0.72, 16000), (800, 0.72, 16000), (900, 0.72, 14000), (1000, 0.72, 12000), (1050, 0.72, 12000), (1150, 0.72, 12000)]:
+                  (700, 0.72, 16000), (800, 0.72, 16000), (900, 0.72, 14000), (1000, 0.72, 12000), (1050, 0.72, 12000), (1150, 0.72, 12000), (2000, 0.72, 6000), (2400, 1.0, 6000)]:
     K = hrf_len(t_r, 20.0)
     y = gen_voxels_device(V, T, t_r, 20.0)
     out = bd_alloc(V, T, K, 100, torch.float32, y.device)
