@@ -298,7 +298,8 @@ def main():
         def step_e2e():
             return pb.bd(y_host, w["t_r"], lbda=w["lbda"], theta_0=w["theta_0"], hrf_dur=w["hrf_dur"],
                          bounds=[w["bounds"]], nb_iter=n)
-        step_e2e()
+        res = step_e2e()     # two untimed calls: the pinned result blocks of two consecutive calls
+        res = step_e2e()     # (the caller still holds the previous result) are then both cached
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):

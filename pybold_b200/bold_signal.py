@@ -174,6 +174,7 @@ def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stoppin
 # ---- host-resident batches: chunked, double-buffered streaming ------------------------------
 _STREAM_MIN_VOXELS = 8192      # below this a single launch is used
 _STREAM_TARGET_CHUNK = 32768   # approximate chunk size, rounded to whole waves of the grid
+_PINNED_RESULT_LIMIT = 4 << 30  # results up to this many bytes are returned in pinned host memory
 _staging_cache = {}
 
 
@@ -207,7 +208,14 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
     shapes = {"x": (chunk, T), "z": (chunk, T), "diff_z": (chunk, T), "h": (chunk, K),
               "theta": (chunk,), "J": (chunk, ntr), "r": (chunk, ntr), "g": (chunk, ntr),
               "n_trace": (chunk,)}
-    final = {k: torch.empty((V,) + shp[1:], dtype=(torch.int32 if k == "n_trace" else dtype))
+    # Results of moderate size are written by the device straight into pinned host tensors (PyTorch
+    # caches pinned blocks, so repeated calls do not pay cudaHostAlloc again); larger ones go through
+    # two pinned staging slots and a host copy into pageable memory.
+    esize = torch.empty((), dtype=dtype).element_size()
+    out_bytes = sum(V * int(np.prod(shp[1:], dtype=np.int64)) * esize for shp in shapes.values())
+    pin_out = out_bytes <= _PINNED_RESULT_LIMIT
+    final = {k: torch.empty((V,) + shp[1:], dtype=(torch.int32 if k == "n_trace" else dtype),
+                            pin_memory=pin_out)
              for k, shp in shapes.items()}
 
     def host_vec(val):
@@ -229,7 +237,7 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
             "z0": torch.empty((chunk, T), dtype=dtype, device=dev) if z0h is not None else None,
             "out": bd_alloc(chunk, T, K, nb_iter, dtype, dev),
             "stage_in": _staging(("in", s_idx, chunk, T, dtype), {"y": (chunk, T), "z0": (chunk, T)}, dtype),
-            "stage_out": _staging(("out", s_idx, chunk, T, K, ntr, dtype), shapes, dtype),
+            "stage_out": None if pin_out else _staging(("out", s_idx, chunk, T, K, ntr, dtype), shapes, dtype),
             "range": None,
         })
 
@@ -238,8 +246,9 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
             return
         lo, hi = slot["range"]
         slot["event"].synchronize()
-        for k in final:
-            final[k][lo:hi].copy_(slot["stage_out"][k][:hi - lo])
+        if not pin_out:
+            for k in final:
+                final[k][lo:hi].copy_(slot["stage_out"][k][:hi - lo])
         slot["range"] = None
 
     main = torch.cuda.current_stream()
@@ -269,7 +278,8 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
             bd_batch(slot["y"][:n], t_r, lb, th, slot["z0"][:n] if z0src is not None else None,
                      hrf_dur, bounds, nb_iter, early_stopping, wind, tol, out=out)
             for k in final:
-                slot["stage_out"][k][:n].copy_(out[k], non_blocking=True)
+                dst = final[k][lo:hi] if pin_out else slot["stage_out"][k][:n]
+                dst.copy_(out[k], non_blocking=True)
             slot["event"].record(st)
         slot["range"] = (lo, hi)
     for slot in slots:
