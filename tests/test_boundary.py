@@ -94,3 +94,24 @@ def test_synth_generator_is_rank_independent():
     a = gen_voxels(6, 50, 1.0, 20.0, seed0=3)
     b = gen_voxels(3, 50, 1.0, 20.0, seed0=3, first_voxel=3)
     assert np.array_equal(a[3:], b)
+
+
+def test_dispatch_covers_every_series_length():
+    """Host-side dispatch (no GPU needed): every T <= 2560 with K <= 28 has a register-tiled FP32 variant
+    whose slots hold the series, and the tuned shapes pick the kernels DESIGN.md names."""
+    from pybold_b200 import _lib
+    for K in (20, 27, 28):
+        for T in list(range(1, 400)) + list(range(400, 2561, 7)) + [2560]:
+            vid = _lib.lib.pb_solver_variant(T, K, 0)
+            assert vid != 0, (T, K)
+            lanes, R, kmax = vid // 1000000, (vid // 1000) % 1000, vid % 1000
+            assert lanes * R >= T and kmax >= K, (T, K, vid)
+            assert lanes * R < 2 * T + 2 * R + 320, (T, K, vid)      # never a grossly oversized variant
+    assert _lib.lib.pb_solver_variant(300, 20, 0) == 16019020        # cfg3: two voxels per warp
+    assert _lib.lib.pb_solver_variant(240, 27, 0) == 16015028        # ICASSP native shape
+    assert _lib.lib.pb_solver_variant(1200, 28, 0) == 64020028       # cfg4: two warps per voxel
+    assert _lib.lib.pb_solver_variant(600, 20, 0) == 32020020
+    assert _lib.lib.pb_solver_variant(150, 20, 0) // 1000000 == 8    # four voxels per warp
+    assert _lib.lib.pb_solver_variant(2000, 28, 0) // 1000000 == 128
+    assert _lib.lib.pb_solver_variant(3000, 20, 0) == 0              # generic kernel
+    assert _lib.lib.pb_solver_variant(300, 40, 0) == 0
