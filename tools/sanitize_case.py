@@ -4,14 +4,31 @@ import numpy as np, torch
 sys.path.insert(0, ".")
 import pybold_b200 as pb
 from pybold_b200.synth import gen_voxels
+from pybold_b200 import convolution as cv
+from pybold_b200.synth import gen_voxels_device
+from pybold_b200.utils import inf_norm, rel_l2_err
+from pybold_b200.io import voxels_from_timeseries
 for (T, t_r, dt) in [(300, 1.0, np.float32), (240, 0.75, np.float32), (600, 1.0, np.float32),
                      (1200, 0.72, np.float32), (100, 1.0, np.float32), (200, 0.5, np.float32),
-                     (300, 1.0, np.float64), (1200, 0.72, np.float64)]:
+                     (150, 1.0, np.float32), (350, 1.0, np.float32), (700, 0.72, np.float32),
+                     (2000, 0.72, np.float32), (300, 1.0, np.float64), (1200, 0.72, np.float64)]:
     y = gen_voxels(5, T, t_r, 20.0, seed0=1).astype(dt)
     out = pb.bd(y, t_r, lbda=1.0, nb_iter=3)
     out = pb.bd(y, t_r, lbda=1.0, nb_iter=6, early_stopping=True, tol=1e-2)
     h, _ = pb.spm_hrf(1.0, t_r, 20.0)
     out = pb.deconv(y, t_r, h.astype(dt), lbda=0.5, nb_iter=12, early_stopping=True, tol=1e-3, x0=np.ones(T, dtype=dt))
     print("ok", T, t_r, dt.__name__, float(np.abs(out[1]).max()))
+# operator kernels (register-resident rows and the shared-memory fallback), N3, N4
+for (V, T, K) in [(7, 300, 20), (5, 1200, 28), (3, 301, 20), (4, 600, 40), (9, 4, 1)]:
+    x = torch.randn(V, T, device="cuda")
+    k = torch.randn(V, K, device="cuda")
+    D = pb.DiscretInteg()
+    H = pb.ConvAndLinear(D, k, dim_in=T)
+    for r in (D.op(x), D.adj(x), cv.simple_convolve(k, x), cv.simple_retro_convolve(k, x), H.op(x), H.adj(x)):
+        assert r.shape == (V, T)
+    print("ops ok", V, T, K)
+y, z, dl = gen_voxels_device(33, 300, return_truth=True)
+e = rel_l2_err(inf_norm(y), inf_norm(z))
+vt = voxels_from_timeseries(torch.randn(300, 65, device="cuda"))
 torch.cuda.synchronize()
-print("done")
+print("done", float(e.mean()), tuple(vt.shape))
