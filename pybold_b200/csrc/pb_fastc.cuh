@@ -25,7 +25,7 @@
 #include "pb_tile.cuh"
 
 // source order of the unrolled tile (pb_tile.cuh), picked with the register-file model on
-// fast_bdc_kernel<float, 20, 28, 2, 6> (cfg4: 1587 -> 1457 modelled cycles per inner iteration)
+// fast_bdc_kernel<float, 20, 28, 2, 6> (cfg4: 1587 -> 1423 modelled cycles per inner iteration; tools/order_search.py cta)
 #ifndef PB_C_CONV_JDESC
 #define PB_C_CONV_JDESC 1
 #endif
@@ -33,7 +33,7 @@
 #define PB_C_CONV_RDESC 0
 #endif
 #ifndef PB_C_CONV_RB
-#define PB_C_CONV_RB 8
+#define PB_C_CONV_RB 5
 #endif
 #ifndef PB_C_CONV_DS
 #define PB_C_CONV_DS 0
