@@ -214,9 +214,19 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
     esize = torch.empty((), dtype=dtype).element_size()
     out_bytes = sum(V * int(np.prod(shp[1:], dtype=np.int64)) * esize for shp in shapes.values())
     pin_out = out_bytes <= _PINNED_RESULT_LIMIT
-    final = {k: torch.empty((V,) + shp[1:], dtype=(torch.int32 if k == "n_trace" else dtype),
-                            pin_memory=pin_out)
-             for k, shp in shapes.items()}
+
+    def alloc_final(pinned):
+        return {k: torch.empty((V,) + shp[1:], dtype=(torch.int32 if k == "n_trace" else dtype),
+                               pin_memory=pinned)
+                for k, shp in shapes.items()}
+
+    try:
+        final = alloc_final(pin_out)
+    except RuntimeError:            # the host refuses to lock that much memory: pageable + staging
+        if not pin_out:
+            raise
+        pin_out = False
+        final = alloc_final(False)
 
     def host_vec(val):
         if isinstance(val, torch.Tensor):
