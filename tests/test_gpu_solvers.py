@@ -174,7 +174,7 @@ def test_hrf_estim_vs_exact_minimiser(golden):
 @pytest.mark.parametrize("T,t_r", [(296, 1.0), (299, 1.0), (304, 1.0), (233, 0.75), (305, 1.0), (64, 1.0),
                                    (600, 1.0), (585, 1.0), (640, 0.75), (1195, 0.72), (1280, 0.72),
                                    (284, 0.7535), (200, 1.0), (209, 0.72), (320, 0.72), (400, 1.0),
-                                   (500, 0.72), (700, 0.72), (900, 0.72), (350, 1.0), (330, 0.72), (650, 1.0), (800, 0.72), (150, 1.0), (100, 0.72), (190, 1.0), (128, 2.0),
+                                   (500, 0.72), (700, 0.72), (900, 0.72), (350, 1.0), (330, 0.72), (340, 1.0), (360, 1.0), (650, 1.0), (800, 0.72), (150, 1.0), (100, 0.72), (190, 1.0), (128, 2.0),
                                    (1050, 0.72)])
 def test_bd_kernel_variants_tail_shapes(T, t_r):
     """Shapes at the edges of the register-tiled variants (group kernel tail, CTA kernel with one
