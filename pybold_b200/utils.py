@@ -54,9 +54,14 @@ def inf_norm(arrays, axis=1):
     from ._array import like_input
     if isinstance(arrays, list):
         return [inf_norm(a, axis=axis) for a in arrays]
+    if np.ndim(arrays) == 3:                      # normalised as a whole, like 1-D (utils.py:131-132)
+        dtype = pick_dtype(arrays)
+        xd = to_device(arrays, dtype)
+        flat = inf_norm(xd.reshape(-1))
+        return like_input(flat.reshape(xd.shape), arrays)
+    if np.ndim(arrays) not in (1, 2):
+        raise ValueError("inf-norm normalization only handle 1D, 2D or 3D arrays")
     dtype, xd, one_d, x2 = _rows(arrays)
-    if xd.dim() > 2:
-        raise ValueError("inf-norm normalization only handle 1D or 2D arrays on the device")
     if not one_d and axis == 0:
         x2 = x2.t().contiguous()
     out = torch.empty_like(x2)

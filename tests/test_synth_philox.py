@@ -106,5 +106,9 @@ def test_inf_norm_matches_reference_rule():
         assert np.max(np.abs(inf_norm(v) - v / (np.max(np.abs(v)) + 1.0e-12))) < tol
         cols = inf_norm(a, axis=0)
         assert np.max(np.abs(cols - a / (np.max(np.abs(a), axis=0, keepdims=True) + 1.0e-12))) < tol
+    cube = rng.randn(3, 4, 5)
+    assert np.max(np.abs(inf_norm(cube) - cube / (np.max(np.abs(cube)) + 1.0e-12))) < 1e-15
+    with pytest.raises(ValueError):
+        inf_norm(np.zeros((2, 2, 2, 2)))
     zero = inf_norm(torch.zeros(3, 8, device="cuda"))
     assert float(zero.abs().max()) == 0.0
