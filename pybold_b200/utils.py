@@ -54,12 +54,13 @@ def inf_norm(arrays, axis=1):
     from ._array import like_input
     if isinstance(arrays, list):
         return [inf_norm(a, axis=axis) for a in arrays]
-    if np.ndim(arrays) == 3:                      # normalised as a whole, like 1-D (utils.py:131-132)
+    nd = arrays.dim() if isinstance(arrays, torch.Tensor) else np.ndim(arrays)
+    if nd == 3:                                   # normalised as a whole, like 1-D (utils.py:131-132)
         dtype = pick_dtype(arrays)
         xd = to_device(arrays, dtype)
         flat = inf_norm(xd.reshape(-1))
         return like_input(flat.reshape(xd.shape), arrays)
-    if np.ndim(arrays) not in (1, 2):
+    if nd not in (1, 2):
         raise ValueError("inf-norm normalization only handle 1D, 2D or 3D arrays")
     dtype, xd, one_d, x2 = _rows(arrays)
     if not one_d and axis == 0:
