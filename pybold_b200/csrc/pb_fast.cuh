@@ -281,7 +281,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
         const double lam = (double)p.lbda[v * p.lbda_stride];
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
-        int n_done = 0;
+        int n_done = 0, ring_pos = 0;
         real res[R];
         for (int k = 0; k < p.nb_iter; ++k) {
             vx.forward(res);
@@ -294,7 +294,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
             vx.adjoint(res, g);
             if (es) {
                 vx.template update<true, false>(g, step, th, beta[k], u, pc, pw);
-                real *slot = ring + (size_t)(k % nring) * R * 32;
+                real *slot = ring + (size_t)ring_pos * R * 32;         // ring_pos = k % nring
 #pragma unroll
                 for (int r = 0; r < R; ++r) slot[r * 32 + lane] = u[r];
             } else {
@@ -310,8 +310,10 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
                     so[r] = 0;
                     sn[r] = vx.w[r];
                 }
+                int pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;     // (k - wind + 2) % nring: oldest u
                 for (int m = 0; m < p.wind - 1; ++m) {
-                    const real *slot = ring + (size_t)((k - p.wind + 2 + m) % nring) * R * 32;
+                    const real *slot = ring + (size_t)pos * R * 32;
+                    pos = pos + 1 == nring ? 0 : pos + 1;
                     const bool is_old = m < p.wind - sub;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
@@ -319,17 +321,18 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
                         if (is_old) so[r] += uu; else sn[r] += uu;
                     }
                 }
-                double pn = 0.0, pd = 0.0;
+                real qn = 0, qd = 0;                  // lane partials in `real`, warp sums in double
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const real mo = so[r] * inv_old, mn = sn[r] * inv_new;
-                    pn += (double)(mn - mo) * (double)(mn - mo);
-                    pd += (double)mn * (double)mn;
+                    qn = fma(mn - mo, mn - mo, qn);
+                    qd = fma(mn, mn, qd);
                 }
-                pn = warp_sum(pn);
-                pd = warp_sum(pd);
+                const double pn = warp_sum((double)qn);
+                const double pd = warp_sum((double)qd);
                 if (sqrt(pn) / (sqrt(pd) + 1.0e-10) < p.tol) break;
             }
+            if (es) ring_pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;
         }
         vx.forward(res);
         if (n_done > 0) {
