@@ -164,6 +164,12 @@ int pb_hrf_estim_f64(const double *z, const double *y, double t_r, double hrf_du
                      double *out_theta, double *out_h, double *out_cost,
                      int64_t V, int T, int K, pb_stream_t stream);
 
+/* Dense Toeplitz matrix of k.conv(.): out[i, c] = k[i - c] for 0 <= i - c < klen, else 0; out is
+ * [dim_out, dim_in] row-major.  pybold/convolution.py:105-132 (`toeplitz_from_kernel`).  The solvers never
+ * form this matrix; it serves callers of the reference's convolution module. */
+int pb_toeplitz_f32(const float *k, int klen, float *out, int64_t dim_out, int64_t dim_in, pb_stream_t stream);
+int pb_toeplitz_f64(const double *k, int klen, double *out, int64_t dim_out, int64_t dim_in, pb_stream_t stream);
+
 /* ---- N3: on-device synthetic voxels and the post-processing of the ICASSP-2019 simulation.
  * pb_synth_voxels: the batch that `examples/icassp_2019/simulation.py:27-48` builds one voxel at a time
  * with `gen_rnd_bloc_bold` (pybold/data.py:243-400): `nb_events` unit boxcars of `blk` samples, the

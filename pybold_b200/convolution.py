@@ -33,18 +33,51 @@ def _run(name, k, x):
     return like_input(out, x)
 
 
+def _resize_last(x, n):
+    """x truncated or zero-padded along its last axis to n samples (host or device array)."""
+    T = x.shape[-1]
+    if n == T:
+        return x
+    if n < T:
+        return x[..., :n]
+    if isinstance(x, torch.Tensor):
+        return torch.nn.functional.pad(x, (0, n - T))
+    import numpy as np
+    pad = [(0, 0)] * (np.ndim(x) - 1) + [(0, n - T)]
+    return np.pad(np.asarray(x), pad)
+
+
 def simple_convolve(k, x, dim_out=None):
-    """out[i] = sum_j k[j] x[i-j] (pybold/convolution.py:135-164)."""
-    if dim_out is not None and dim_out != (x.shape[-1]):
-        raise NotImplementedError("only square (dim_out == len(x)) convolutions are on the hot path")
-    return _run("pb_conv_op", k, x)
+    """out[i] = sum_j k[j] x[i-j], i < dim_out (pybold/convolution.py:135-164); dim_out defaults to len(x)."""
+    T = x.shape[-1]
+    if dim_out is None or dim_out == T:
+        return _run("pb_conv_op", k, x)
+    if dim_out > T:                      # outputs past the input: x continues with zeros
+        return _run("pb_conv_op", k, _resize_last(x, dim_out))
+    return _resize_last(_run("pb_conv_op", k, x), dim_out)
 
 
 def simple_retro_convolve(k, x, dim_out=None):
-    """out[i] = sum_j k[j] x[i+j] (pybold/convolution.py:167-196)."""
-    if dim_out is not None and dim_out != (x.shape[-1]):
-        raise NotImplementedError("only square (dim_out == len(x)) convolutions are on the hot path")
-    return _run("pb_conv_adj", k, x)
+    """out[i] = sum_j k[j] x[i+j], i < dim_out (pybold/convolution.py:167-196); dim_out defaults to len(x)."""
+    T = x.shape[-1]
+    if dim_out is None or dim_out == T:
+        return _run("pb_conv_adj", k, x)
+    if dim_out > T:
+        return _run("pb_conv_adj", k, _resize_last(x, dim_out))
+    return _resize_last(_run("pb_conv_adj", k, x), dim_out)
+
+
+def toeplitz_from_kernel(k, dim_in, dim_out=None):
+    """Dense ``[dim_out, dim_in]`` Toeplitz matrix of ``k.conv(.)`` (pybold/convolution.py:105-132):
+    ``K[i, c] = k[i - c]``.  The solvers never build it; provided for callers of the reference module."""
+    if dim_out is None:
+        dim_out = dim_in
+    dtype = pick_dtype(k)
+    kd = to_device(k, dtype).reshape(-1)
+    out = torch.empty((int(dim_out), int(dim_in)), dtype=dtype, device=kd.device)
+    rc = _lib.fn("pb_toeplitz", dtype)(ptr(kd), kd.numel(), ptr(out), int(dim_out), int(dim_in), stream_ptr())
+    _lib.check(rc, "pb_toeplitz")
+    return like_input(out, k)
 
 
 def spectral_convolve(k, x):

@@ -258,6 +258,17 @@ int run_transpose(const real *in, real *out, int64_t rows, int64_t cols, pb_stre
 }
 
 template <typename real>
+int run_toeplitz(const real *k, int klen, real *out, int64_t dim_out, int64_t dim_in, pb_stream_t stream) {
+    if (dim_out == 0 || dim_in == 0) return PB_OK;
+    if (!k || !out || klen <= 0 || dim_out < 0 || dim_in < 0) return PB_ERR_INVALID_ARG;
+    const int64_t gx = (dim_in + 255) / 256;
+    if (gx > 2147483647LL) return PB_ERR_UNSUPPORTED;
+    const unsigned gy = (unsigned)(dim_out < 65535 ? dim_out : 65535);
+    pb::toeplitz_kernel<real><<<dim3((unsigned)gx, gy), 256, 0, (cudaStream_t)stream>>>(k, klen, out, dim_out, dim_in);
+    return last_error();
+}
+
+template <typename real>
 int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
     if (a.V == 0) return PB_OK;
     if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz || !a.out_J ||
@@ -514,6 +525,10 @@ int pb_hrf_len(double t_r, double dur) {
     int pb_rel_l2_err_##SUF(const REAL *est, const REAL *ref, int64_t ref_stride, REAL *out_err,       \
                             int64_t V, int T, pb_stream_t s) {                                         \
         return run_rel_l2_err<REAL>(est, ref, ref_stride, out_err, V, T, s);                           \
+    }                                                                                                  \
+    int pb_toeplitz_##SUF(const REAL *k, int klen, REAL *out, int64_t dim_out, int64_t dim_in,         \
+                          pb_stream_t s) {                                                             \
+        return run_toeplitz<REAL>(k, klen, out, dim_out, dim_in, s);                                   \
     }                                                                                                  \
     int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
                            const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \

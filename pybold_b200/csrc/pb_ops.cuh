@@ -269,6 +269,20 @@ __global__ void __launch_bounds__(256) transpose_kernel(const real *__restrict__
         }
 }
 
+// Dense Toeplitz matrix of k.conv(.) (pybold/convolution.py:105-132): K[i, c] = k[i - c] for
+// 0 <= i - c < len(k), else 0; [dim_out, dim_in] row-major.  The solvers never form it;
+// it exists for callers of the reference's convolution module.  Write-only, HBM bound.
+template <typename real>
+__global__ void toeplitz_kernel(const real *__restrict__ k, int klen, real *out, int64_t dim_out, int64_t dim_in) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = blockIdx.y; i < dim_out; i += gridDim.y) {
+        if (c < dim_in) {
+            const int64_t d = i - c;
+            out[i * dim_in + c] = (d >= 0 && d < klen) ? k[d] : real(0);
+        }
+    }
+}
+
 // hrf_estim / the theta step alone (pybold/bold_signal.py:217-239, :329-334)
 template <typename real>
 __global__ void hrf_estim_kernel(const real *z, const real *y, HrfGrid grid, const real *theta0,

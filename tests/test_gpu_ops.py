@@ -191,3 +191,36 @@ def test_row_kernels_in_place_and_misaligned():
     out = torch.empty(V * T + 1, device="cuda", dtype=torch.float32)
     assert _lib.lib.pb_integ_op_f32(buf.data_ptr() + 4, out.data_ptr() + 4, V, T, 0) == 0
     assert rel(out[1:].reshape(V, T).cpu().numpy(), want) < 3e-5
+
+
+def test_toeplitz_and_rectangular_convolutions_like_the_reference_tests():
+    """pybold/tests/test_convolution.py:169-211: the Toeplitz matrix with the block signal as kernel
+    (rectangular, dim_in = len(hrf)) reproduces the direct convolution and its adjoint."""
+    import pybold_b200 as pb
+    from pybold_b200 import convolution as cv
+    rng = np.random.RandomState(21)
+    for (T, K) in [(300, 20), (600, 30), (128, 7)]:
+        ai_s = np.zeros(T)
+        ai_s[rng.randint(0, T - 20, 4)] = 1.0
+        ai_s = np.cumsum(ai_s) % 2.0                      # block signal
+        hrf = pb.spm_hrf(1.0, 1.0, float(K), True)[0]
+        assert len(hrf) == K
+        H = cv.toeplitz_from_kernel(ai_s, len(hrf), len(ai_s))
+        assert H.shape == (T, K)
+        want = np.zeros((T, K))
+        for i in range(T):
+            for c in range(K):
+                if 0 <= i - c < T:
+                    want[i, c] = ai_s[i - c]
+        assert np.array_equal(H, want)
+        ar_ref = cv.simple_convolve(hrf, ai_s)
+        assert np.allclose(ar_ref, H.dot(hrf), atol=1.0e-7)
+        adj_ref = cv.simple_retro_convolve(ai_s, H.dot(hrf), len(hrf))
+        assert adj_ref.shape == (K,)
+        assert np.allclose(adj_ref, H.T.dot(H.dot(hrf)), atol=1.0e-7)
+        # square case and dim_out > len(x)
+        Hs = cv.toeplitz_from_kernel(hrf, T)
+        assert np.allclose(Hs.dot(ai_s), cv.simple_convolve(hrf, ai_s), atol=1.0e-12)
+        assert np.allclose(Hs.T.dot(ai_s), cv.simple_retro_convolve(hrf, ai_s), atol=1.0e-12)
+        longer = cv.simple_convolve(hrf, ai_s[:50], 55)
+        assert longer.shape == (55,) and np.allclose(longer, np.convolve(hrf, ai_s[:50])[:55], atol=1e-12)
