@@ -41,19 +41,24 @@ class ConvAndLinear:
     """
 
     def __init__(self, M, kernel, dim_in, dim_out=None, spectral_conv=False):
-        if dim_out is not None and dim_out != dim_in:
-            raise NotImplementedError("only square operators (dim_out == dim_in) are on the hot path")
         self.M = M
         self.k = kernel
         self.dim_in = dim_in
+        self.dim_out = dim_in if dim_out is None else dim_out
         self.spectral_conv = spectral_conv
 
     def op(self, x):
+        if self.dim_out != self.dim_in:          # rectangular Toeplitz (linear.py:69): not on the hot path
+            from .convolution import simple_convolve
+            return simple_convolve(self.k, self.M.op(x), self.dim_out)
         if isinstance(self.M, DiscretInteg):
             return _conv_run("pb_hrfinteg_op", self.k, x)
         return _conv_run("pb_conv_op", self.k, self.M.op(x))
 
     def adj(self, x):
+        if self.dim_out != self.dim_in:
+            from .convolution import simple_retro_convolve
+            return self.M.adj(simple_retro_convolve(self.k, x, self.dim_in))
         if isinstance(self.M, DiscretInteg):
             return _conv_run("pb_hrfinteg_adj", self.k, x)
         return self.M.adj(_conv_run("pb_conv_adj", self.k, x))

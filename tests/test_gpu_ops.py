@@ -224,3 +224,17 @@ def test_toeplitz_and_rectangular_convolutions_like_the_reference_tests():
         assert np.allclose(Hs.T.dot(ai_s), cv.simple_retro_convolve(hrf, ai_s), atol=1.0e-12)
         longer = cv.simple_convolve(hrf, ai_s[:50], 55)
         assert longer.shape == (55,) and np.allclose(longer, np.convolve(hrf, ai_s[:50])[:55], atol=1e-12)
+
+
+def test_rectangular_conv_and_linear_matches_dense_toeplitz():
+    """ConvAndLinear with dim_out != dim_in (pybold/linear.py:46-113) against K.dot(cumsum) / revcumsum(K.T.dot)."""
+    import pybold_b200 as pb
+    from pybold_b200 import convolution as cv
+    rng = np.random.RandomState(22)
+    for (dim_in, dim_out, K) in [(120, 100, 20), (100, 130, 12)]:
+        k, x, yv = rng.randn(K), rng.randn(dim_in), rng.randn(dim_out)
+        H = pb.ConvAndLinear(pb.DiscretInteg(), k, dim_in, dim_out)
+        Kmat = cv.toeplitz_from_kernel(k, dim_in, dim_out)
+        assert np.allclose(H.op(x), Kmat.dot(np.cumsum(x)), atol=1e-11)
+        assert np.allclose(H.adj(yv), np.cumsum(Kmat.T.dot(yv)[::-1])[::-1], atol=1e-11)
+        assert abs(np.dot(H.op(x), yv) - np.dot(x, H.adj(yv))) < 1e-9
