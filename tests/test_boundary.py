@@ -115,3 +115,25 @@ def test_dispatch_covers_every_series_length():
     assert _lib.lib.pb_solver_variant(2000, 28, 0) // 1000000 == 128
     assert _lib.lib.pb_solver_variant(3000, 20, 0) == 0              # generic kernel
     assert _lib.lib.pb_solver_variant(300, 40, 0) == 0
+
+
+def test_db3_highpass_filter_has_its_defining_properties():
+    """The db3 decomposition high-pass used by `mad_daub_noise_est` (pybold/utils.py:16-25) cannot be pinned
+    against PyWavelets here (not installed); its coefficients are pinned by what defines the filter: unit
+    energy, three vanishing moments, orthogonality to its even shifts, and the quadrature-mirror relation to a
+    low-pass that sums to sqrt(2).  (The boundary convention of pywt's symmetric mode stays unverified; the
+    MAD of the detail coefficients is insensitive to it.)"""
+    from pybold_b200.noise import _DB3_DEC_HI
+    g = np.array(_DB3_DEC_HI)
+    k = np.arange(len(g))
+    assert abs(np.sum(g * g) - 1.0) < 1e-10                    # (tabulated to ~12 digits)
+    for m in range(3):
+        assert abs(np.sum(k ** m * g)) < 1e-10, m
+    assert abs(np.sum(k ** 3 * g)) > 1e-2                      # exactly three vanishing moments
+    for shift in (2, 4):
+        assert abs(np.sum(g[shift:] * g[:-shift])) < 1e-10
+    lo = g[::-1] * (-1.0) ** k                                 # quadrature mirror
+    assert abs(abs(np.sum(lo)) - np.sqrt(2.0)) < 1e-10
+    for shift in (0, 2, 4):
+        hi_s = np.concatenate([np.zeros(shift), g])[:len(g)]
+        assert abs(np.sum(lo * hi_s)) < 1e-10
