@@ -36,6 +36,16 @@ def mad_daub_noise_est(y, c=0.6744):
     return (mad / c).reshape(-1)
 
 
+def mad(x, c=0.6744):
+    """Median absolute deviation of each row (pybold/utils.py:10-13); 1-D input gives a scalar tensor."""
+    x2 = x.reshape(1, -1) if x.dim() == 1 else x
+    n = x2.shape[1]
+    med = x2.median(dim=1, keepdim=True).values if n % 2 else _median(x2)
+    dev = (x2 - med).abs()
+    out = (dev.median(dim=1, keepdim=True).values if n % 2 else _median(dev)) / c
+    return out.reshape(()) if x.dim() == 1 else out.reshape(-1)
+
+
 def _median(a):
     """NumPy-style median (mean of the two middle values for an even count)."""
     s, _ = torch.sort(a, dim=1)

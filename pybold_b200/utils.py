@@ -8,6 +8,7 @@ import torch
 from . import _lib
 from ._array import pick_dtype, ptr, stream_ptr, to_device
 from .linear import ConvAndLinear, DiscretInteg
+from .noise import mad, mad_daub_noise_est  # noqa: F401  (same module as in the reference, pybold/utils.py:10-25)
 
 
 def spectral_radius_est(L, x_shape, nb_iter=30, tol=1.0e-6, verbose=False, x0=None):
