@@ -90,3 +90,19 @@ def rel_l2_err(est, ref):
     rc = _lib.fn("pb_rel_l2_err", dtype)(ptr(e2), ptr(r2), stride, ptr(out), V, T, stream_ptr())
     _lib.check(rc, "pb_rel_l2_err")
     return like_input(out, est)
+
+
+class Tracker:
+    """Iterate callback that records ``f(x, *args)`` (pybold/utils.py:27-45), for user code that still
+    drives a SciPy optimiser; the device theta solver does not go through iterate callbacks."""
+
+    def __init__(self, f, args, verbose=0):
+        self.f, self.args, self.verbose = f, list(args), verbose
+        self.J, self.idx = [], 0
+
+    def __call__(self, x):
+        self.idx += 1
+        value = self.f(x, *self.args)
+        if self.verbose > 2:
+            print("At iterate {0}, tracked function = {1:.6f}".format(self.idx, value))
+        self.J.append(value)
