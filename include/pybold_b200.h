@@ -193,6 +193,18 @@ int pb_rel_l2_err_f32(const float *est, const float *ref, int64_t ref_stride, fl
 int pb_rel_l2_err_f64(const double *est, const double *ref, int64_t ref_stride, double *out_err,
                       int64_t V, int T, pb_stream_t stream);
 
+/* ---- N1: one outer iteration of the noise-constrained lambda loop of `deconv(lbda=None)`
+ * (pybold/bold_signal.py:139-162) for the whole batch: voxels with active[v] != 0 take the new inner-loop
+ * result (x, z, w <- xn, zn, wn), then r[v] = ||x - y||^2, g[v] = ||w||_1,
+ * alpha[v] += mu (r[v] - T sigma[v]^2) (active voxels only) and lbda[v] = 1 / (2 alpha[v]). */
+int pb_noise_step_f32(const float *xn, const float *zn, const float *wn, const float *y, const float *sigma,
+                      const unsigned char *active, double mu, float *x, float *z, float *w, float *alpha,
+                      float *lbda, float *out_r, float *out_g, int64_t V, int T, pb_stream_t stream);
+int pb_noise_step_f64(const double *xn, const double *zn, const double *wn, const double *y,
+                      const double *sigma, const unsigned char *active, double mu, double *x, double *z,
+                      double *w, double *alpha, double *lbda, double *out_r, double *out_g, int64_t V, int T,
+                      pb_stream_t stream);
+
 /* ---- N4: layout adapter between the reference pipeline's time-major voxel matrices [T, V]
  * (`NiftiMasker.fit_transform`, consumed as `voxels.T`, examples/icassp_2019/validation.py:90-103)
  * and the solvers' [V, T]: out[c, r] = in[r, c] for an in[rows, cols] row-major matrix.  Out of place

@@ -54,6 +54,7 @@ _OPS = {
               c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,
               c_int64, c_int, c_int, _P],
     "pb_transpose": [_P, _P, c_int64, c_int64, _P],
+    "pb_noise_step": [_P, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P],
     "pb_toeplitz": [_P, c_int, _P, c_int64, c_int64, _P],
     "pb_synth_voxels": [c_uint64, c_int64, c_double, c_double, c_double, c_int, c_int, c_double, c_double,
                         _P, _P, _P, c_int64, c_int, _P],

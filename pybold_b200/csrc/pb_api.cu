@@ -396,6 +396,22 @@ int run_rel_l2_err(const real *est, const real *ref, int64_t ref_stride, real *o
     return last_error();
 }
 
+template <typename real>
+int run_noise_step(const real *xn, const real *zn, const real *wn, const real *y, const real *sigma,
+                   const unsigned char *active, double mu, real *x, real *z, real *w, real *alpha, real *lbda,
+                   real *out_r, real *out_g, int64_t V, int T, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!xn || !zn || !wn || !y || !sigma || !active || !x || !z || !w || !alpha || !lbda || !out_r || !out_g ||
+        V < 0 || T <= 0)
+        return PB_ERR_INVALID_ARG;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int64_t need = (V + 7) / 8, cap = (int64_t)d.sm_count * 8;
+    pb::noise_step_kernel<real><<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(
+        xn, zn, wn, y, sigma, active, mu, x, z, w, alpha, lbda, out_r, out_g, V, T);
+    return last_error();
+}
+
 __global__ void fma_peak_kernel(float *sink, int iters) {
     float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
     float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -529,6 +545,13 @@ int pb_hrf_len(double t_r, double dur) {
     int pb_toeplitz_##SUF(const REAL *k, int klen, REAL *out, int64_t dim_out, int64_t dim_in,         \
                           pb_stream_t s) {                                                             \
         return run_toeplitz<REAL>(k, klen, out, dim_out, dim_in, s);                                   \
+    }                                                                                                  \
+    int pb_noise_step_##SUF(const REAL *xn, const REAL *zn, const REAL *wn, const REAL *y,             \
+                            const REAL *sigma, const unsigned char *active, double mu, REAL *x, REAL *z, \
+                            REAL *w, REAL *alpha, REAL *lbda, REAL *out_r, REAL *out_g, int64_t V,     \
+                            int T, pb_stream_t s) {                                                    \
+        return run_noise_step<REAL>(xn, zn, wn, y, sigma, active, mu, x, z, w, alpha, lbda, out_r,     \
+                                    out_g, V, T, s);                                                   \
     }                                                                                                  \
     int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
                            const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \

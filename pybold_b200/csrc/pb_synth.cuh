@@ -198,4 +198,56 @@ __global__ void rel_l2_err_kernel(const real *__restrict__ est, const real *__re
     }
 }
 
+// One outer iteration of the noise-constrained lambda loop of deconv(lbda=None)
+// (pybold/bold_signal.py:139-162), fused over the batch: voxels still active take the new inner-loop
+// result, then r = ||x - y||^2, g = ||diff_z||_1, alpha += mu (r - T sigma^2), lbda = 1 / (2 alpha).
+// One warp per voxel, rows read once and (for active voxels) written once.
+template <typename real>
+__global__ void noise_step_kernel(const real *__restrict__ xn, const real *__restrict__ zn,
+                                  const real *__restrict__ wn, const real *__restrict__ y,
+                                  const real *__restrict__ sigma, const unsigned char *__restrict__ active,
+                                  double mu, real *x, real *z, real *w, real *alpha, real *lbda,
+                                  real *out_r, real *out_g, int64_t V, int T) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nwarp) {
+        const bool on = active[v] != 0;
+        real sr = 0, sg = 0;
+        for (int i = lane; i < T; i += 32) {
+            const int64_t o = v * T + i;
+            real xv, wv;
+            if (on) {
+                xv = xn[o];
+                wv = wn[o];
+                x[o] = xv;
+                w[o] = wv;
+                z[o] = zn[o];
+            } else {
+                xv = x[o];
+                wv = w[o];
+            }
+            const real d = xv - y[o];
+            sr = fma(d, d, sr);
+            sg += fabs(wv);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            sr += __shfl_xor_sync(PB_FULL, sr, s);
+            sg += __shfl_xor_sync(PB_FULL, sg, s);
+        }
+        if (lane == 0) {
+            real a = alpha[v];
+            if (on) {
+                const real sgm = sigma[v];
+                a = a + (real)mu * (sr - (real)T * sgm * sgm);
+                alpha[v] = a;
+            }
+            lbda[v] = real(1) / (real(2) * a);
+            out_r[v] = sr;
+            out_g[v] = sg;
+        }
+    }
+}
+
 }  // namespace pb

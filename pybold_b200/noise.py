@@ -13,7 +13,8 @@ from __future__ import annotations
 
 import torch
 
-from ._array import like_input
+from . import _lib
+from ._array import like_input, ptr, stream_ptr
 
 _DB3_DEC_HI = (-0.3326705529509569, 0.8068915093133388, -0.4598775021193313,
                -0.13501102001039084, 0.08544127388224149, 0.035226291882100656)
@@ -65,26 +66,25 @@ def deconv_auto_lbda(y_in, yb, one_d, hrf, lipschitz, sigma, early_stopping, tol
     lbda = 1.0 / (2.0 * alpha)
     mu = 1.0e-4
     w = torch.zeros_like(yb)
-    active = torch.ones(V, dtype=torch.bool, device=dev)
+    x = torch.zeros_like(yb)
+    z = torch.zeros_like(yb)
+    active = torch.ones(V, dtype=torch.uint8, device=dev)
     sub = int(wind / 2)
     hist = []
     J, R, G = [], [], []
-    x = z = None
+    step = _lib.fn("pb_noise_step", dtype)
     for i in range(nb_iter):
         x_n, z_n, w_n, _, _ = deconv_batch(yb, hrf, lbda, lipschitz, w, early_stopping, tol, wind,
                                            nb_sub_iter)
-        keep = active[:, None]
-        w = torch.where(keep, w_n, w)
-        x = x_n if x is None else torch.where(keep, x_n, x)
-        z = z_n if z is None else torch.where(keep, z_n, z)
-        r = torch.sum((x - yb) ** 2, dim=1)
-        grad = r - T * sigma ** 2                                   # bold_signal.py:143
-        alpha = torch.where(active, alpha + mu * grad, alpha)
-        lbda = 1.0 / (2.0 * alpha)
+        r = torch.empty(V, dtype=dtype, device=dev)
+        g = torch.empty(V, dtype=dtype, device=dev)
+        # bold_signal.py:139-145: keep the result of the active voxels, r, g, alpha and lambda updates
+        rc = step(ptr(x_n), ptr(z_n), ptr(w_n), ptr(yb), ptr(sigma), ptr(active), mu, ptr(x), ptr(z), ptr(w),
+                  ptr(alpha), ptr(lbda), ptr(r), ptr(g), V, T, stream_ptr())
+        _lib.check(rc, "pb_noise_step")
         hist.append(alpha.clone())
         if len(hist) > wind:
             hist = hist[1:]
-        g = torch.sum(w.abs(), dim=1)
         R.append(r)
         G.append(g)
         J.append(0.5 * r + lbda * g)
@@ -92,7 +92,7 @@ def deconv_auto_lbda(y_in, yb, one_d, hrf, lipschitz, sigma, early_stopping, tol
             old_it = torch.stack(hist[:-sub]).mean(dim=0)
             new_it = torch.stack(hist[-sub:]).mean(dim=0)
             stop = (new_it - old_it).abs() / new_it.abs() < tol
-            active = active & ~stop
+            active = active & (~stop).to(torch.uint8)
             if not bool(active.any()):
                 break
     # bold_signal.py:180-212: last deconvolution with the final lambda
