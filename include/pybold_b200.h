@@ -89,6 +89,15 @@ int pb_spm_hrf_f32(const float *theta, double t_r, double dur, int normalized,
                    float *out_h, int64_t V, int K, pb_stream_t stream);
 int pb_spm_hrf_f64(const double *theta, double t_r, double dur, int normalized,
                    double *out_h, int64_t V, int K, pb_stream_t stream);
+/* Same with the shape parameters of the reference's signature (hrf_model.py:12-14):
+ * shape7 (HOST pointer, read during the call) = {dt, p_delay, undershoot, p_disp, u_disp,
+ * p_u_ratio, onset}; K = pb_hrf_len_ex(t_r, dur, dt).  Like the reference, the time axis is
+ * shifted by onset / dt (hrf_model.py:25). */
+int pb_hrf_len_ex(double t_r, double dur, double dt);
+int pb_spm_hrf_ex_f32(const float *theta, double t_r, double dur, int normalized,
+                      const double *shape7, float *out_h, int64_t V, int K, pb_stream_t stream);
+int pb_spm_hrf_ex_f64(const double *theta, double t_r, double dur, int normalized,
+                      const double *shape7, double *out_h, int64_t V, int K, pb_stream_t stream);
 
 /* ---- A4: spectral_radius_est (pybold/utils.py:94-109) ---------------------------------
  * Power iteration on A^T A, A = conv(h) o cumsum, from the supplied start x0 (the reference
@@ -193,6 +202,19 @@ int pb_rel_l2_err_f32(const float *est, const float *ref, int64_t ref_stride, fl
 int pb_rel_l2_err_f64(const double *est, const double *ref, int64_t ref_stride, double *out_err,
                       int64_t V, int T, pb_stream_t stream);
 
+/* ---- A8 / N1: noise level of `deconv(lbda=None)` (pybold/utils.py:10-25, called at
+ * pybold/bold_signal.py:103).  pb_mad: out[v] = median(|x_v - median(x_v)|) / c for the rows of
+ * x[V, n] (`mad`, utils.py:10-13).  pb_mad_daub_noise_est: the same statistic of the level-1 db3
+ * detail coefficients of y[V, T] (PyWavelets "symmetric" extension, floor((T + 5) / 2)
+ * coefficients; T < 10 has no level-1 decomposition and takes the series itself, the reference's
+ * `except ValueError` branch, utils.py:23-24).  Medians are exact order statistics. */
+int pb_mad_f32(const float *x, double c, float *out, int64_t V, int n, pb_stream_t stream);
+int pb_mad_f64(const double *x, double c, double *out, int64_t V, int n, pb_stream_t stream);
+int pb_mad_daub_noise_est_f32(const float *y, double c, float *out_sigma, int64_t V, int T,
+                              pb_stream_t stream);
+int pb_mad_daub_noise_est_f64(const double *y, double c, double *out_sigma, int64_t V, int T,
+                              pb_stream_t stream);
+
 /* ---- N1: one outer iteration of the noise-constrained lambda loop of `deconv(lbda=None)`
  * (pybold/bold_signal.py:139-162) for the whole batch: voxels with active[v] != 0 take the new inner-loop
  * result (x, z, w <- xn, zn, wn), then r[v] = ||x - y||^2, g[v] = ||w||_1,
@@ -213,9 +235,9 @@ int pb_transpose_f32(const float *in, float *out, int64_t rows, int64_t cols, pb
 int pb_transpose_f64(const double *in, double *out, int64_t rows, int64_t cols, pb_stream_t stream);
 
 /* ---- measurement utility (not part of the reference API) --------------------------------
- * FP32 FMA-pipe microbenchmark used as the roofline denominator: launches
- * `blocks` CTAs of 256 threads, each thread running 8 independent chains of `iters` FFMA.
- * Executed flops = blocks * 256 * 8 * iters * 2.  `sink` must hold blocks*256 floats. */
+ * FP32 FMA-pipe microbenchmark reported beside the nominal roofline: launches
+ * `blocks` CTAs of 256 threads (use 4 per SM), each thread running 16 independent chains of
+ * `iters` FFMA.  Executed flops = blocks * 256 * 16 * iters * 2.  `sink` holds blocks*256 floats. */
 int pb_bench_fma_f32(float *sink, int blocks, int iters, pb_stream_t stream);
 
 #ifdef __cplusplus

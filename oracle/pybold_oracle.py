@@ -151,6 +151,39 @@ def spm_hrf_closed_form(delta, t_r, dur, dt=0.001):
     return np.where(pos, g6 - 0.167 * g16, 0.0)
 
 
+def _gamma_pdf(s, a, loc):
+    """scipy.stats.gamma.pdf(s, a, loc=loc) in closed form: x^(a-1) e^(-x) / Gamma(a), x = s - loc."""
+    x = np.asarray(s, dtype=np.float64) - loc
+    pos = x > 0
+    xp = np.where(pos, x, 1.0)
+    val = np.exp((a - 1.0) * np.log(xp) - xp - math.lgamma(a))
+    at_zero = 0.0 if a > 1.0 else (1.0 if a == 1.0 else np.inf)
+    return np.where(pos, val, np.where(x == 0, at_zero, 0.0))
+
+
+def spm_hrf_general(delta, t_r=1.0, dur=60.0, normalized_hrf=True, dt=0.001, p_delay=6,
+                    undershoot=16.0, p_disp=1.0, u_disp=1.0, p_u_ratio=0.167, onset=0.0):
+    """pybold/hrf_model.py:12-39 for ANY shape parameters, evaluated only where it is needed (the
+    kept samples, plus one pass over the fine grid for the normalisation maximum) -- the statement of
+    what ``pb_spm_hrf_ex_*`` computes.  Note the reference's ``t = linspace(...) - onset / dt``
+    (hrf_model.py:25): the onset is divided by dt, so ``onset = 0.004`` shifts the HRF by 4 s."""
+    n_fine = int(float(dur) / dt)
+    stride = int(t_r / dt)
+    t_step = float(dur) / (n_fine - 1)
+
+    def at(idx):
+        t = idx.astype(np.float64) * t_step - float(onset) / dt
+        s = float(delta) * t
+        return (_gamma_pdf(s, p_delay / p_disp, dt / p_disp)
+                - p_u_ratio * _gamma_pdf(s, undershoot / u_disp, dt / u_disp)), t
+
+    h, t = at(np.arange(0, n_fine, stride))
+    if normalized_hrf:
+        fine, _ = at(np.arange(n_fine))
+        h = h / np.max(fine + 1.0e-30)
+    return h, t
+
+
 # --------------------------------------------------------------------------------------
 # A4: power-iteration Lipschitz estimate
 # --------------------------------------------------------------------------------------
@@ -309,6 +342,29 @@ def theta_step_lbfgsb(theta_prev, z, y, t_r, hrf_dur, bounds):
     theta, _, _ = fmin_l_bfgs_b(func=hrf_fit_err, x0=theta_prev, args=(z, y, t_r, hrf_dur),
                                 bounds=bounds, approx_grad=True, maxiter=999, pgtol=1.0e-12)
     return theta
+
+
+def hrf_estim(z, y, t_r, dur):
+    """pybold/bold_signal.py:225-239: theta from x0 = MAX_DELTA (SciPy clips it to the upper
+    bound 1.9), ``maxiter=99999``; J lists the cost at every L-BFGS-B iterate (the reference's
+    ``Tracker`` callback, utils.py:27-45).  Returns (h, J, theta)."""
+    args = (z, y, t_r, dur)
+    bounds = [(MIN_DELTA + 1.0e-1, MAX_DELTA - 1.0e-1)]
+    J = []
+    theta, _, _ = fmin_l_bfgs_b(func=hrf_fit_err, x0=MAX_DELTA, args=args, bounds=bounds,
+                                approx_grad=True, callback=lambda th: J.append(hrf_fit_err(th, *args)),
+                                maxiter=99999, pgtol=1.0e-12)
+    h, _ = spm_hrf(theta, t_r, dur, False)
+    return h, J, float(np.asarray(theta).reshape(-1)[0])
+
+
+def hrf_estim_exact(z, y, t_r, dur):
+    """The device algorithm for the same problem: the exact bounded minimiser from the clipped start.
+    Returns (h, [cost at the start, cost at the minimiser], theta)."""
+    bounds = [(MIN_DELTA + 1.0e-1, MAX_DELTA - 1.0e-1)]
+    theta = theta_step_exact(MAX_DELTA, z, y, t_r, dur, bounds)
+    h = spm_hrf_closed_form(theta, t_r, dur)
+    return h, [hrf_fit_err_fast(bounds[0][1], z, y, t_r, dur), hrf_fit_err_fast(theta, z, y, t_r, dur)], theta
 
 
 def hrf_taps_and_derivs(theta, t_r, hrf_dur, dt=0.001):
@@ -513,29 +569,51 @@ _DB3_DEC_HI = np.array([-0.3326705529509569, 0.8068915093133388, -0.459877502119
                         -0.13501102001039084, 0.08544127388224149, 0.035226291882100656])
 
 
-def db3_detail_level1(x):
-    """Level-1 db3 detail coefficients, half-sample symmetric extension.
+_DB1_DEC_HI = np.array([-0.7071067811865476, 0.7071067811865476])
 
-    UNPINNED: PyWavelets is absent here, so this follows pywt's documented convention
-    (``cD[o] = sum_j dec_hi[j] x_ext[2 o + 1 - j]``, ``len = floor((T + 5) / 2)``) without a
-    reference vector to check it against.  pybold/utils.py:16-25 calls ``pywt.wavedec``.
+
+def dwt_detail_level1(x, dec_hi):
+    """Level-1 detail coefficients with PyWavelets' default ``symmetric`` (half-sample) extension:
+    ``cD[o] = sum_j dec_hi[j] x_ext[2 o + 1 - j]``, ``len = floor((T + F - 1) / 2)``,
+    ``x_ext[-1 - k] = x[k]``, ``x_ext[T + k] = x[T - 1 - k]``.
+
+    PARTLY PINNED: PyWavelets is absent here (pybold/utils.py:22 calls ``pywt.wavedec``).  The
+    convention (phase ``2 o + 1``, output length, mirror rule) is checked in
+    tests/test_oracle_golden.py against the Haar examples of PyWavelets' documentation
+    (``pywt.dwt([1, 2, 3, 4, 5, 6], 'db1')`` and the odd-length ``[1, 2, 3]`` case, quoted from the
+    documentation, not generated here); the db3 coefficients are pinned by the filter's defining
+    properties (tests/test_boundary.py).  No PyWavelets db3 output vector exists in this repo.
     """
     x = np.asarray(x, dtype=np.float64)
+    dec_hi = np.asarray(dec_hi, dtype=np.float64)
     T = len(x)
-    F = len(_DB3_DEC_HI)
-    ext = np.concatenate([x[:F - 1][::-1], x, x[-(F - 1):][::-1]])
+    F = len(dec_hi)
+    ext = np.concatenate([x[:F - 1][::-1], x, x[-(F - 1):][::-1]]) if F > 1 else x
     n_out = (T + F - 1) // 2
     out = np.empty(n_out)
     for o in range(n_out):
         idx = 2 * o + 1 + (F - 1)     # position in ext of x_ext[2o+1]
-        out[o] = sum(_DB3_DEC_HI[j] * ext[idx - j] for j in range(F))
+        out[o] = sum(dec_hi[j] * ext[idx - j] for j in range(F))
     return out
 
 
+def db3_detail_level1(x):
+    """``pywt.wavedec(x, 'db3', level=1)[1]`` restated (see :func:`dwt_detail_level1`)."""
+    return dwt_detail_level1(x, _DB3_DEC_HI)
+
+
+def mad(x, c=0.6744):
+    """pybold/utils.py:10-13."""
+    return np.median(np.abs(x - np.median(x))) / c
+
+
 def mad_daub_noise_est(x, c=0.6744):
-    """pybold/utils.py:10-25 on top of :func:`db3_detail_level1` (UNPINNED, see there)."""
-    cD = db3_detail_level1(x)
-    return np.median(np.abs(cD - np.median(cD))) / c
+    """pybold/utils.py:16-25.  Series shorter than 10 scans have ``dwt_max_level == 0``: PyWavelets
+    < 1.0 raised ValueError for ``level=1`` there and the reference falls back to ``level=0``, whose
+    only coefficient array is the series itself (utils.py:23-24)."""
+    x = np.asarray(x, dtype=np.float64)
+    cD = x if len(x) < 10 else db3_detail_level1(x)
+    return mad(cD, c)
 
 
 def deconv_auto_lbda(y, hrf, sigma, x0_power=None, lipschitz=None, early_stopping=True,

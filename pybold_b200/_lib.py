@@ -46,6 +46,7 @@ _OPS = {
     "pb_hrfinteg_op": [_P, c_int64, _P, _P, c_int64, c_int, c_int, _P],
     "pb_hrfinteg_adj": [_P, c_int64, _P, _P, c_int64, c_int, c_int, _P],
     "pb_spm_hrf": [_P, c_double, c_double, c_int, _P, c_int64, c_int, _P],
+    "pb_spm_hrf_ex": [_P, c_double, c_double, c_int, ctypes.POINTER(c_double), _P, c_int64, c_int, _P],
     "pb_lipschitz_power": [_P, c_int64, _P, c_int64, c_int, c_double, _P, c_int64, c_int, c_int, _P],
     "pb_lipschitz_frob": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
     "pb_deconv": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_double,
@@ -55,6 +56,8 @@ _OPS = {
               c_int64, c_int, c_int, _P],
     "pb_transpose": [_P, _P, c_int64, c_int64, _P],
     "pb_noise_step": [_P, _P, _P, _P, _P, _P, c_double, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P],
+    "pb_mad": [_P, c_double, _P, c_int64, c_int, _P],
+    "pb_mad_daub_noise_est": [_P, c_double, _P, c_int64, c_int, _P],
     "pb_toeplitz": [_P, c_int, _P, c_int64, c_int64, _P],
     "pb_synth_voxels": [c_uint64, c_int64, c_double, c_double, c_double, c_int, c_int, c_double, c_double,
                         _P, _P, _P, c_int64, c_int, _P],
@@ -71,6 +74,7 @@ _PLAIN = {
     "pb_error_string": ([c_int], c_char_p),
     "pb_solver_variant": ([c_int, c_int, c_int], c_int),
     "pb_hrf_len": ([c_double, c_double], c_int),
+    "pb_hrf_len_ex": ([c_double, c_double, c_double], c_int),
     "pb_bd_wave_voxels": ([c_int, c_int, c_int, c_int], c_int),
     "pb_bench_fma_f32": ([_P, c_int, c_int, _P], c_int),
 }

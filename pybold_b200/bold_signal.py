@@ -45,7 +45,15 @@ def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e
     dtype, dev = y.dtype, y.device
     hrf = hrf.to(device=dev, dtype=dtype).contiguous()
     K = hrf.shape[-1]
+    if hrf.dim() > 2 or (hrf.dim() == 2 and hrf.shape[0] not in (1, V)):
+        raise ValueError("hrf must be [K] (shared) or [V, K] with V = %d voxels, got %s"
+                         % (V, tuple(hrf.shape)))
     h_stride = 0 if hrf.dim() == 1 or hrf.shape[0] == 1 else K
+    if w0 is not None:
+        if tuple(w0.shape) != (V, T) or w0.dtype != dtype or w0.device != dev:
+            raise ValueError("w0 must be a %s tensor of shape (%d, %d) on %s" % (dtype, V, T, dev))
+        w0 = w0.contiguous()
+    y = y.contiguous()
     lb, lb_stride = per_voxel(lbda, V, dtype, dev, "lbda")
     Lc, L_stride = per_voxel(lipschitz, V, dtype, dev, "lipschitz")
     x = torch.empty_like(y)
@@ -53,10 +61,11 @@ def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e
     dz = torch.empty_like(y)
     J = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
     n_iter = torch.zeros(V, dtype=torch.int32, device=dev)
-    rc = _lib.fn("pb_deconv", dtype)(
-        ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0),
-        int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
-        ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
+    with torch.cuda.device(dev):        # the C side sizes its grid for, and launches on, the current device
+        rc = _lib.fn("pb_deconv", dtype)(
+            ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0),
+            int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
+            ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
     _lib.check(rc, "pb_deconv")
     return x, z, dz, J, n_iter
 
@@ -67,9 +76,10 @@ def deconv(y, t_r, hrf, lbda=None, early_stopping=True, tol=1.0e-6,  # noqa
 
     Returns ``(x, z, diff_z, J, R, G)`` like the reference: with a float ``lbda`` J is the cost
     trace normalised by its first entry and R, G are None (bold_signal.py:97).  ``lbda=None``
-    (noise-constrained lambda, bold_signal.py:99-214) needs the noise level: pass ``sigma=``
-    (the reference takes it from a PyWavelets db3 MAD estimate, utils.py:16-25).
-    Extra keyword arguments: ``x0`` (power-iteration start), ``dtype``.
+    (noise-constrained lambda, bold_signal.py:99-214) estimates the noise level like the reference
+    (db3 MAD, utils.py:16-25, on the device) unless ``sigma=`` is given.
+    Extra keyword arguments: ``x0`` (power-iteration start), ``sigma``, ``dtype``.  float64 input
+    (the reference's type) selects the FP64 build, float32 input or ``dtype=np.float32`` the FP32 one.
     """
     dtype = pick_dtype(y, hrf, dtype=dtype)
     yb, one_d = _as_batch(y, dtype)
@@ -162,11 +172,14 @@ def bd_batch(y, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, early_stoppin
     lo, hi = bounds[0]
     if out is None:
         out = bd_alloc(V, T, K, nb_iter, dtype, dev)
-    rc = _lib.fn("pb_bd", dtype)(
-        ptr(y), float(t_r), float(hrf_dur), ptr(lb), lb_stride, ptr(th0), th_stride, ptr(z_0),
-        float(lo), float(hi), int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
-        ptr(out["x"]), ptr(out["z"]), ptr(out["diff_z"]), ptr(out["h"]), ptr(out["theta"]),
-        ptr(out["J"]), ptr(out["r"]), ptr(out["g"]), ptr(out["n_trace"]), V, T, K, stream_ptr())
+    if z_0 is not None and (tuple(z_0.shape) != (V, T) or z_0.dtype != dtype or z_0.device != dev):
+        raise ValueError("z_0 must be a %s tensor of shape (%d, %d) on %s" % (dtype, V, T, dev))
+    with torch.cuda.device(dev):        # grid sizing and the launch stream follow the current device
+        rc = _lib.fn("pb_bd", dtype)(
+            ptr(y), float(t_r), float(hrf_dur), ptr(lb), lb_stride, ptr(th0), th_stride, ptr(z_0),
+            float(lo), float(hi), int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
+            ptr(out["x"]), ptr(out["z"]), ptr(out["diff_z"]), ptr(out["h"]), ptr(out["theta"]),
+            ptr(out["J"]), ptr(out["r"]), ptr(out["g"]), ptr(out["n_trace"]), V, T, K, stream_ptr())
     _lib.check(rc, "pb_bd")
     return out
 
@@ -179,7 +192,10 @@ _staging_cache = {}
 
 
 def _staging(key, shapes, dtype):
-    """Pinned staging buffers, cached across calls (cudaHostAlloc is expensive)."""
+    """Pinned staging buffers, cached across calls (cudaHostAlloc is expensive).  The cache is keyed
+    by thread and device: one thread per GPU in the same process must not share staging slots."""
+    import threading
+    key = (threading.get_ident(), torch.cuda.current_device()) + tuple(key)
     bufs = _staging_cache.get(key)
     if bufs is None:
         if len(_staging_cache) > 8:
@@ -246,7 +262,9 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
             "y": torch.empty((chunk, T), dtype=dtype, device=dev),
             "z0": torch.empty((chunk, T), dtype=dtype, device=dev) if z0h is not None else None,
             "out": bd_alloc(chunk, T, K, nb_iter, dtype, dev),
-            "stage_in": _staging(("in", s_idx, chunk, T, dtype), {"y": (chunk, T), "z0": (chunk, T)}, dtype),
+            "stage_in": _staging(("in", s_idx, chunk, T, dtype, z0h is not None),
+                                 {"y": (chunk, T), "z0": (chunk, T)} if z0h is not None else {"y": (chunk, T)},
+                                 dtype),
             "stage_out": None if pin_out else _staging(("out", s_idx, chunk, T, K, ntr, dtype), shapes, dtype),
             "range": None,
         })
@@ -303,6 +321,11 @@ def bd(y, t_r, lbda=1.0, theta_0=None, z_0=None, hrf_dur=20.0,  # noqa
        bounds=None, nb_iter=100, nb_sub_iter=1000, nb_last_iter=10000,
        print_period=50, early_stopping=False, wind=4, tol=1.0e-12, verbose=0, dtype=None):
     """Semi-blind deconvolution with the dilated SPM HRF (pybold/bold_signal.py:281-382).
+
+    Precision follows the input like NumPy would: float64 arrays (what the reference computes in,
+    bold_signal.py:288) run the FP64 build -- the parity build, about 2.3x slower -- and float32
+    arrays the FP32 build the throughput figures are quoted on (1e-4 of the reference, DESIGN.md);
+    ``dtype=np.float32`` forces the fast build for float64 input.
 
     Returns ``(x, z, diff_z, h, d)``; ``d`` has the reference's keys ``'J'``, ``'r'``, ``'g'``
     (length ``nb_iter + 2``, shorter after an early stop) and ``'l_alpha'`` (empty list), plus

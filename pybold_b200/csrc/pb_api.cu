@@ -9,6 +9,7 @@
 #include "pb_fast_registry.h"
 #include "pb_ops.cuh"
 #include "pb_ops_rows.cuh"
+#include "pb_noise.cuh"
 #include "pb_synth.cuh"
 
 #define PB_VERSION 100   /* 0.1.0 */
@@ -78,10 +79,10 @@ int last_error() {
     return e == cudaSuccess ? PB_OK : (int)e;
 }
 
-pb::HrfGrid make_grid(double t_r, double dur, int *n_fine) {
+pb::HrfGrid make_grid(double t_r, double dur, int *n_fine, double dt = 0.001) {
     pb::HrfGrid g;
-    const int N = (int)(dur / 0.001);        // int(float(dur) / dt), hrf_model.py:25
-    const int stride = (int)(t_r / 0.001);   // int(t_r / dt),       hrf_model.py:36
+    const int N = (int)(dur / dt);           // int(float(dur) / dt), hrf_model.py:25
+    const int stride = (int)(t_r / dt);      // int(t_r / dt),       hrf_model.py:36
     g.t_step = dur / (double)(N - 1);
     g.stride = stride;
     g.K = stride > 0 ? (N + stride - 1) / stride : 0;
@@ -201,6 +202,37 @@ int run_spm_hrf(const real *theta, double t_r, double dur, int normalized, real 
     int grid = (int)(need < (int64_t)d.sm_count * 8 ? need : (int64_t)d.sm_count * 8);
     pb::spm_hrf_kernel<real><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(theta, g, n_fine,
                                                                             normalized, out_h, V);
+    return last_error();
+}
+
+template <typename real>
+int run_spm_hrf_ex(const real *theta, double t_r, double dur, int normalized, const double *shape7,
+                   real *out_h, int64_t V, int K, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!theta || !out_h || !shape7 || V < 0) return PB_ERR_INVALID_ARG;
+    const double dt = shape7[0], p_delay = shape7[1], undershoot = shape7[2], p_disp = shape7[3],
+                 u_disp = shape7[4], ratio = shape7[5], onset = shape7[6];
+    if (!(dt > 0.0) || !(t_r >= dt) || !(dur > 2.0 * dt) || !(p_disp > 0.0) || !(u_disp > 0.0) ||
+        !(p_delay > 0.0) || !(undershoot > 0.0))
+        return PB_ERR_INVALID_ARG;
+    int n_fine = 0;
+    pb::HrfGrid g = make_grid(t_r, dur, &n_fine, dt);
+    if (K != g.K) return PB_ERR_INVALID_ARG;
+    pb::HrfShape sh;
+    sh.dt = dt;
+    sh.a_peak = p_delay / p_disp;
+    sh.loc_peak = dt / p_disp;
+    sh.a_under = undershoot / u_disp;
+    sh.loc_under = dt / u_disp;
+    sh.ratio = ratio;
+    sh.t_shift = onset / dt;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int warps = 4;
+    int64_t need = (V + warps - 1) / warps;
+    int grid = (int)(need < (int64_t)d.sm_count * 8 ? need : (int64_t)d.sm_count * 8);
+    pb::spm_hrf_ex_kernel<real><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(theta, g, sh, n_fine,
+                                                                               normalized, out_h, V);
     return last_error();
 }
 
@@ -412,16 +444,45 @@ int run_noise_step(const real *xn, const real *zn, const real *wn, const real *y
     return last_error();
 }
 
-__global__ void fma_peak_kernel(float *sink, int iters) {
-    float a0 = threadIdx.x * 1e-9f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
-    float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
-    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
-#pragma unroll 4
-    for (int i = 0; i < iters; ++i) {
-        a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
-        a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+template <typename real, int MODE>
+int run_mad(const real *x, double c, real *out, int64_t V, int T, pb_stream_t stream) {
+    if (V == 0) return PB_OK;
+    if (!x || !out || V < 0 || T <= 0 || !(c > 0.0)) return PB_ERR_INVALID_ARG;
+    DeviceInfo d = device_info();
+    if (d.err) return d.err;
+    const int nmax = MODE == 1 ? pb::noise_detail_len(T) : T;
+    const size_t warp_bytes = (size_t)nmax * sizeof(double);
+    if (warp_bytes > (size_t)d.max_smem_optin) return PB_ERR_UNSUPPORTED;
+    int warps = (int)((size_t)d.max_smem_optin / 2 / warp_bytes);
+    warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
+    const size_t smem = (size_t)warps * warp_bytes;
+    auto kern = pb::mad_rows_kernel<real, MODE>;
+    int e = set_smem(kern, smem);
+    if (e) return e;
+    const int64_t need = (V + warps - 1) / warps, cap = (int64_t)d.sm_count * 2;
+    kern<<<(int)(need < cap ? need : cap), warps * 32, smem, (cudaStream_t)stream>>>(x, c, out, V, T, nmax);
+    return last_error();
+}
+
+// FP32 FMA-pipe ceiling: 16 independent chains a = a * m + c per thread (one register read per FFMA, the
+// multiplier and the addend sit in the operand-reuse cache); launch with 4 CTAs of 256 threads per SM.
+// Best of the variants in tools/exp_fma.cu (profiles/r01_fma_microbench.txt: 70.7 Tflop/s of 74.4 nominal).
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *sink, int iters) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-9f + 0.5f * i;
+    const float m0 = 0.999f + blockIdx.x * 1e-9f, m1 = 0.998f, c0 = 1e-3f, c1 = 2e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            a[i] = fmaf(a[i], m0, c0);
+            a[i + 1] = fmaf(a[i + 1], m1, c1);
+        }
     }
-    sink[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r += a[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 }  // namespace
@@ -462,6 +523,11 @@ int pb_hrf_len(double t_r, double dur) {
     return make_grid(t_r, dur, nullptr).K;
 }
 
+int pb_hrf_len_ex(double t_r, double dur, double dt) {
+    if (!(dt > 0.0) || !(t_r >= dt) || !(dur > 2.0 * dt)) return PB_ERR_INVALID_ARG;
+    return make_grid(t_r, dur, nullptr, dt).K;
+}
+
 #define PB_DEFINE_OPS(SUF, REAL)                                                                       \
     int pb_integ_op_##SUF(const REAL *x, REAL *out, int64_t V, int T, pb_stream_t s) {                 \
         return run_op<REAL, pb::OP_INTEG>(nullptr, 0, x, out, V, T, 0, s);                             \
@@ -488,6 +554,10 @@ int pb_hrf_len(double t_r, double dur) {
     int pb_spm_hrf_##SUF(const REAL *theta, double t_r, double dur, int normalized, REAL *out_h,       \
                          int64_t V, int K, pb_stream_t s) {                                            \
         return run_spm_hrf<REAL>(theta, t_r, dur, normalized, out_h, V, K, s);                         \
+    }                                                                                                  \
+    int pb_spm_hrf_ex_##SUF(const REAL *theta, double t_r, double dur, int normalized,                 \
+                            const double *shape7, REAL *out_h, int64_t V, int K, pb_stream_t s) {      \
+        return run_spm_hrf_ex<REAL>(theta, t_r, dur, normalized, shape7, out_h, V, K, s);              \
     }                                                                                                  \
     int pb_lipschitz_power_##SUF(const REAL *h, int64_t hs, const REAL *x0, int64_t xs, int nb_iter,   \
                                  double tol, REAL *out_L, int64_t V, int T, int K, pb_stream_t s) {    \
@@ -552,6 +622,13 @@ int pb_hrf_len(double t_r, double dur) {
                             int T, pb_stream_t s) {                                                    \
         return run_noise_step<REAL>(xn, zn, wn, y, sigma, active, mu, x, z, w, alpha, lbda, out_r,     \
                                     out_g, V, T, s);                                                   \
+    }                                                                                                  \
+    int pb_mad_##SUF(const REAL *x, double c, REAL *out, int64_t V, int n, pb_stream_t s) {            \
+        return run_mad<REAL, 0>(x, c, out, V, n, s);                                                   \
+    }                                                                                                  \
+    int pb_mad_daub_noise_est_##SUF(const REAL *y, double c, REAL *out_sigma, int64_t V, int T,        \
+                                    pb_stream_t s) {                                                   \
+        return run_mad<REAL, 1>(y, c, out_sigma, V, T, s);                                             \
     }                                                                                                  \
     int pb_hrf_estim_##SUF(const REAL *z, const REAL *y, double t_r, double hrf_dur,                   \
                            const REAL *theta0, int64_t theta0_stride, double lo, double hi,            \

@@ -181,6 +181,46 @@ __global__ void spm_hrf_kernel(const real *theta, HrfGrid grid, int n_fine, int 
     }
 }
 
+// spm_hrf with arbitrary shape parameters (pybold/hrf_model.py:12-14, :25-31): the default-parameter
+// kernel above uses integer powers; here g(s; a, loc) = exp((a - 1) log x - x - lgamma(a)), x = s - loc.
+struct HrfShape {
+    double dt, a_peak, loc_peak, a_under, loc_under, ratio, t_shift;   // t_shift = onset / dt (:25)
+};
+
+__device__ __forceinline__ double gamma_pdf_general(double s, double a, double loc, double lg) {
+    const double x = s - loc;
+    if (x > 0.0) return exp((a - 1.0) * log(x) - x - lg);
+    if (x == 0.0) return a > 1.0 ? 0.0 : (a == 1.0 ? 1.0 : INFINITY);
+    return x == x ? 0.0 : x;
+}
+
+template <typename real>
+__global__ void spm_hrf_ex_kernel(const real *theta, HrfGrid grid, HrfShape sh, int n_fine, int normalized,
+                                  real *out_h, int64_t V) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double lg_p = lgamma(sh.a_peak), lg_u = lgamma(sh.a_under);
+    auto value = [&](double th, double t) {
+        const double s = th * (t - sh.t_shift);
+        return gamma_pdf_general(s, sh.a_peak, sh.loc_peak, lg_p) -
+               sh.ratio * gamma_pdf_general(s, sh.a_under, sh.loc_under, lg_u);
+    };
+    for (int64_t v = (int64_t)blockIdx.x * nwarp + warp; v < V; v += (int64_t)gridDim.x * nwarp) {
+        const double th = (double)theta[v];
+        double scale = 1.0;
+        if (normalized) {                                   // max over the FINE grid, hrf_model.py:33-34
+            double mx = -1.0e300;
+            for (int n = lane; n < n_fine; n += 32) mx = fmax(mx, value(th, (double)n * grid.t_step) + 1.0e-30);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(PB_FULL, mx, o));
+            scale = mx;
+        }
+        for (int a = lane; a < grid.K; a += 32) {
+            const double hh = value(th, grid.t(a));
+            out_h[v * grid.K + a] = (real)(normalized ? hh / scale : hh);
+        }
+    }
+}
+
 // spectral_radius_est (pybold/utils.py:94-109) with the start vector supplied.
 template <typename real>
 __global__ void lipschitz_power_kernel(const real *h, int64_t h_stride, const real *x0,

@@ -18,16 +18,20 @@ def hrf_len(t_r, dur):
     return K
 
 
+_DEFAULT_SHAPE = (0.001, 6, 16.0, 1.0, 1.0, 0.167, 0.0)
+
+
 def spm_hrf(delta, t_r=1.0, dur=60.0, normalized_hrf=True, dt=0.001, p_delay=6,
             undershoot=16.0, p_disp=1.0, u_disp=1.0, p_u_ratio=0.167, onset=0.0):
     """Same signature and return as ``pybold.hrf_model.spm_hrf`` (hrf_model.py:12-39).
 
-    ``delta`` may also be a length-V array / tensor: the result is then ``[V, K]``.
-    Only the reference's default shape parameters are compiled into the kernel.
+    ``delta`` may also be a length-V array / tensor: the result is then ``[V, K]``.  The
+    reference's default shape parameters run on the integer-power kernel the solvers use
+    (``pb_spm_hrf_*``), any other combination on ``pb_spm_hrf_ex_*``.  Like the reference the
+    time axis is shifted by ``onset / dt`` (hrf_model.py:25), i.e. ``onset=0.004`` means 4 s.
     """
-    if (dt, p_delay, undershoot, p_disp, u_disp, p_u_ratio, onset) != (0.001, 6, 16.0, 1.0, 1.0, 0.167, 0.0):
-        raise NotImplementedError("pybold_b200.spm_hrf supports the reference's default "
-                                  "dt / delay / dispersion / ratio / onset only")
+    import ctypes
+    shape = (dt, p_delay, undershoot, p_disp, u_disp, p_u_ratio, onset)
     require_cuda()
     scalar = not isinstance(delta, torch.Tensor) and np.ndim(delta) == 0
     dtype = pick_dtype(delta) if not scalar else torch.float64
@@ -41,12 +45,21 @@ def spm_hrf(delta, t_r=1.0, dur=60.0, normalized_hrf=True, dt=0.001, p_delay=6,
         raise ValueError("delta should belong in [{0}, {1}]; wich correspond to a max FWHM of "
                          "10.52s and a min FWHM of 2.80s, got delta = {2}".format(
                              MIN_DELTA, MAX_DELTA, lo if lo < MIN_DELTA else hi))
-    K = hrf_len(t_r, dur)
     V = th.numel()
-    out = torch.empty((V, K), dtype=dtype, device=dev)
-    rc = _lib.fn("pb_spm_hrf", dtype)(ptr(th), float(t_r), float(dur), int(bool(normalized_hrf)),
-                                      ptr(out), V, K, stream_ptr())
-    _lib.check(rc, "pb_spm_hrf")
+    if tuple(float(v) for v in shape) == tuple(float(v) for v in _DEFAULT_SHAPE):
+        K = hrf_len(t_r, dur)
+        out = torch.empty((V, K), dtype=dtype, device=dev)
+        rc = _lib.fn("pb_spm_hrf", dtype)(ptr(th), float(t_r), float(dur), int(bool(normalized_hrf)),
+                                          ptr(out), V, K, stream_ptr())
+        _lib.check(rc, "pb_spm_hrf")
+    else:
+        K = _lib.lib.pb_hrf_len_ex(float(t_r), float(dur), float(dt))
+        _lib.check(min(K, 0), "pb_hrf_len_ex")
+        out = torch.empty((V, K), dtype=dtype, device=dev)
+        shape7 = (ctypes.c_double * 7)(*[float(v) for v in shape])
+        rc = _lib.fn("pb_spm_hrf_ex", dtype)(ptr(th), float(t_r), float(dur), int(bool(normalized_hrf)),
+                                             shape7, ptr(out), V, K, stream_ptr())
+        _lib.check(rc, "pb_spm_hrf_ex")
     n_fine = int(float(dur) / dt)
     t_hrf = (np.linspace(0, dur, n_fine) - float(onset) / dt)[::int(t_r / dt)]
     if scalar:

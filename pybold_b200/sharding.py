@@ -18,25 +18,63 @@ def voxel_range(n_voxels, rank, world_size):
     return (rank * n_voxels) // world_size, ((rank + 1) * n_voxels) // world_size
 
 
-def gather_rows(local, n_voxels, group=None):
-    """All-gather row slabs of unequal height into the full ``[V, ...]`` tensor on every rank.
+def row_heights(n_voxels, world_size):
+    return [voxel_range(n_voxels, r, world_size)[1] - voxel_range(n_voxels, r, world_size)[0]
+            for r in range(world_size)]
 
-    Slabs are padded to the largest height so that one ``all_gather_into_tensor`` suffices.
+
+def gather_rows(local, n_voxels, group=None, out=None):
+    """All-gather the per-rank row slabs into the full ``[V, ...]`` tensor on every rank.
+
+    Equal slabs (the usual case: V divisible by the world size) are ONE ``all_gather_into_tensor``
+    straight into the result -- no padding, no concatenation, the result is written once.  Unequal
+    slabs (they differ by at most one row) go as one grouped batch of sends / receives, every
+    receive landing in its final rows.  ``out`` lets a caller reuse the result tensor.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    heights = [voxel_range(n_voxels, r, world)[1] - voxel_range(n_voxels, r, world)[0]
-               for r in range(world)]
+    heights = row_heights(n_voxels, world)
     if local.shape[0] != heights[rank]:
         raise ValueError("rank %d holds %d rows, expected %d" % (rank, local.shape[0], heights[rank]))
-    hmax = max(heights)
     tail = tuple(local.shape[1:])
-    padded = local.new_zeros((hmax,) + tail)
-    padded[:local.shape[0]] = local
-    full = local.new_empty((world * hmax,) + tail)
-    dist.all_gather_into_tensor(full, padded.contiguous(), group=group)
-    full = full.reshape((world, hmax) + tail)
-    return torch.cat([full[r, :heights[r]] for r in range(world)], dim=0)
+    if out is None:
+        out = local.new_empty((n_voxels,) + tail)
+    elif tuple(out.shape) != (n_voxels,) + tail or out.dtype != local.dtype or not out.is_contiguous():
+        raise ValueError("out must be a contiguous %s tensor of shape %s" % (local.dtype, (n_voxels,) + tail))
+    local = local.contiguous()
+    if world == 1:
+        out.copy_(local)
+        return out
+    if min(heights) == max(heights):
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    ops = []
+    for r in range(world):
+        lo, hi = voxel_range(n_voxels, r, world)
+        if r == rank:
+            out[lo:hi].copy_(local)
+            continue
+        peer = dist.get_global_rank(group, r) if group is not None else r
+        if heights[rank] > 0:
+            ops.append(dist.P2POp(dist.isend, local, peer, group))
+        if hi > lo:
+            ops.append(dist.P2POp(dist.irecv, out[lo:hi], peer, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
+
+
+ALL_OUTPUTS = ("x", "z", "diff_z", "h", "theta", "J", "r", "g")   # SURVEY.md 8(e)
+
+
+def gather_outputs(out, n_voxels, keys=ALL_OUTPUTS, group=None, into=None):
+    """Gather the named outputs of a ``bd_batch`` result dict; ``into`` (a dict from a previous call)
+    reuses the full-size tensors."""
+    res = {} if into is None else into
+    for k in keys:
+        res[k] = gather_rows(out[k], n_voxels, group, out=res.get(k))
+    return res
 
 
 def bd_sharded(y_full_or_local, n_voxels, solve, gather=True, group=None):

@@ -230,11 +230,113 @@ def gen_fit_err():
          t_r=np.array(t_r), dur=np.array(dur))
 
 
+def gen_bd_t1200():
+    """cfg4 shape (T = 1200, TR = 0.72, K = 28) with the reference's own nb_iter = 100 (about 25 s)."""
+    out, tags = {}, ["t1200_n100"]
+    y1200 = gen_voxels(2, 1200, 0.72, 20.0, seed0=43)
+    x, z, dz, h, d, rec = run_bd(y1200[1], 0.72, lbda=1.7, theta_0=2.0, hrf_dur=20.0, nb_iter=100)
+    tag = tags[0]
+    out["y_" + tag], out["t_r_" + tag] = y1200[1], np.array(0.72)
+    out["lbda_" + tag], out["theta_0_" + tag] = np.array(1.7), np.array(2.0)
+    out["hrf_dur_" + tag], out["nb_iter_" + tag] = np.array(20.0), np.array(100)
+    out["x_" + tag], out["z_" + tag], out["dz_" + tag], out["h_" + tag] = x, z, dz, h
+    out["J_" + tag], out["r_" + tag], out["g_" + tag] = d["J"], d["r"], d["g"]
+    out["thetas_" + tag] = np.array(rec.thetas)
+    out["nfev_" + tag] = np.array(rec.nfev)
+    print(tag, "theta_end", rec.thetas[-1], "J_end", d["J"][-1])
+    save("bd_t1200", tags=np.array(tags), **out)
+
+
+def gen_deconv_auto():
+    """``deconv(lbda=None)`` (bold_signal.py:99-214) of the live reference.  PyWavelets is absent, so
+    ``mad_daub_noise_est`` -- the name ``bold_signal`` imported -- is replaced by a function that
+    returns the STORED sigma; everything else is the reference's own code."""
+    out, tags = {}, []
+    orig = ref_bs.mad_daub_noise_est
+
+    def add(tag, y, t_r, h, sigma, seed, **kw):
+        np.random.seed(seed)
+        x0 = np.random.randn(len(y))
+        np.random.seed(seed)
+        ref_bs.mad_daub_noise_est = lambda x, c=0.6744: sigma
+        try:
+            x, z, dz, J, R, G = quiet(ref_bs.deconv, y.copy(), t_r, h, lbda=None, **kw)
+        finally:
+            ref_bs.mad_daub_noise_est = orig
+        tags.append(tag)
+        out["y_" + tag], out["h_" + tag], out["x0_" + tag] = y, h, x0
+        out["t_r_" + tag], out["sigma_" + tag] = np.array(t_r), np.array(sigma)
+        for key, default in (("nb_iter", 1000), ("nb_sub_iter", 1000), ("early_stopping", True),
+                             ("tol", 1.0e-6), ("wind", 6)):
+            out[key + "_" + tag] = np.array(kw.get(key, default))
+        out["x_" + tag], out["z_" + tag], out["dz_" + tag] = x, z, dz
+        out["J_" + tag], out["R_" + tag], out["G_" + tag] = np.array(J), np.array(R), np.array(G)
+        print(tag, "outer iterations", len(J), "J_end", J[-1])
+
+    y300 = gen_voxels(3, 300, 1.0, 20.0, seed0=61)
+    h20, _ = ref_hm.spm_hrf(1.0, 1.0, 20.0, True)
+    # a: no early stopping at all, every loop runs to its count
+    add("a", y300[0], 1.0, h20, 0.35, 300, nb_iter=12, nb_sub_iter=60, early_stopping=False)
+    # b: inner early stops (Q5 window) and the alpha window stop both fire
+    add("b", y300[1], 1.0, h20, 0.5, 301, nb_iter=60, nb_sub_iter=300, early_stopping=True,
+        tol=3.0e-2, wind=6)
+    # c: another window length, tighter tolerance: inner stops, outer runs out
+    add("c", y300[2], 1.0, h20, 0.2, 302, nb_iter=15, nb_sub_iter=200, early_stopping=True,
+        tol=2.0e-3, wind=4)
+    # d: the shape of examples/synth_data/deconv.py (cfg1: T = 600, TR = 1, HRF of 30 s at delta 1.5)
+    y600 = gen_voxels(1, 600, 1.0, 30.0, seed0=71)
+    h30, _ = ref_hm.spm_hrf(1.5, 1.0, 30.0, True)
+    add("d", y600[0], 1.0, h30, 0.4, 303, nb_iter=40, nb_sub_iter=150, early_stopping=True,
+        tol=5.0e-3, wind=6)
+    # e: alpha window stop with wind = 4
+    add("e", y300[1], 1.0, h20, 1.0, 304, nb_iter=60, nb_sub_iter=300, early_stopping=True,
+        tol=2.0e-2, wind=4)
+    save("deconv_auto", tags=np.array(tags), **out)
+
+
+def gen_hrf_estim():
+    """``hrf_estim`` (bold_signal.py:225-239): h and the Tracker's cost per L-BFGS-B iterate."""
+    out, tags = {}, []
+    for tag, T, t_r, dur, seed in (("a", 300, 1.0, 20.0, 81), ("b", 240, 0.75, 20.0, 82),
+                                   ("c", 600, 1.0, 30.0, 83)):
+        y, z_true, _ = gen_voxels(1, T, t_r, dur, seed0=seed, return_truth=True)
+        h, J = ref_bs.hrf_estim(z_true[0], y[0], t_r, dur)
+        tags.append(tag)
+        out["y_" + tag], out["z_" + tag] = y[0], z_true[0]
+        out["t_r_" + tag], out["dur_" + tag] = np.array(t_r), np.array(dur)
+        out["h_" + tag], out["J_" + tag] = h, np.array(J, dtype=np.float64).reshape(-1)
+        print(tag, "iterates", len(J), "J_end", float(np.asarray(J[-1]).reshape(-1)[0]))
+    save("hrf_estim", tags=np.array(tags), **out)
+
+
+HRF_PARAM_GRID = [
+    dict(delta=1.0, t_r=1.0, dur=20.0, p_delay=5, undershoot=15.0),
+    dict(delta=0.8, t_r=0.75, dur=25.0, p_disp=0.9, u_disp=1.2, p_u_ratio=0.3),
+    dict(delta=1.4, t_r=2.0, dur=32.0, onset=0.5),        # onset / dt = 500 s: identically zero taps
+    dict(delta=1.4, t_r=2.0, dur=32.0, onset=0.004),      # shifted by 4 s
+    dict(delta=0.7, t_r=1.0, dur=20.0, onset=-0.002, p_delay=5.5),
+    dict(delta=1.0, t_r=0.5, dur=20.0, dt=0.002),
+    dict(delta=1.9, t_r=0.3, dur=18.0, p_delay=7, undershoot=12.0, p_disp=1.1, u_disp=0.8,
+         p_u_ratio=0.1, onset=0.001),
+]
+
+
+def gen_hrf_params():
+    """``spm_hrf`` with non-default shape parameters (hrf_model.py:12-39)."""
+    out = {"n": np.array(len(HRF_PARAM_GRID))}
+    for idx, kw in enumerate(HRF_PARAM_GRID):
+        for norm, key in ((False, "h"), (True, "hn")):
+            h, t = ref_hm.spm_hrf(normalized_hrf=norm, **kw)
+            out["%s%d" % (key, idx)] = h
+        out["t%d" % idx] = t
+        out["kw%d" % idx] = np.array(sorted(kw.items()), dtype=object).astype(str)
+    save("spm_hrf_params", **out)
+
+
+GENERATORS = {"ops": gen_ops, "spm_hrf": gen_hrf, "lipschitz": gen_lipschitz, "deconv_fixed": gen_deconv,
+              "loops_deconv": gen_loops, "hrf_fit_err": gen_fit_err, "bd": gen_bd, "bd_t1200": gen_bd_t1200,
+              "deconv_auto": gen_deconv_auto, "hrf_estim": gen_hrf_estim, "spm_hrf_params": gen_hrf_params}
+
 if __name__ == "__main__":
-    gen_ops()
-    gen_hrf()
-    gen_lipschitz()
-    gen_deconv()
-    gen_loops()
-    gen_fit_err()
-    gen_bd()
+    for name in (sys.argv[1:] or list(GENERATORS)):
+        GENERATORS[name]()

@@ -238,3 +238,24 @@ def test_rectangular_conv_and_linear_matches_dense_toeplitz():
         assert np.allclose(H.op(x), Kmat.dot(np.cumsum(x)), atol=1e-11)
         assert np.allclose(H.adj(yv), np.cumsum(Kmat.T.dot(yv)[::-1])[::-1], atol=1e-11)
         assert abs(np.dot(H.op(x), yv) - np.dot(x, H.adj(yv))) < 1e-9
+
+
+def test_spm_hrf_shape_parameters_vs_reference_golden(golden):
+    """Non-default delay / dispersion / ratio / onset / dt (pybold/hrf_model.py:12-14) on `pb_spm_hrf_ex_*`."""
+    import pybold_b200 as pb
+    g = golden("spm_hrf_params")
+    for i in range(int(g["n"])):
+        kw = {k: float(v) for k, v in g["kw%d" % i]}
+        for norm, key in ((False, "h"), (True, "hn")):
+            h, t = pb.spm_hrf(normalized_hrf=norm, **kw)
+            want = g["%s%d" % (key, i)]
+            assert h.shape == want.shape and np.array_equal(t, g["t%d" % i])
+            assert np.max(np.abs(h - want)) <= 1e-12 * (np.max(np.abs(want)) + 1e-300), (i, norm)
+    # batched theta, and the default parameters spelled out take the fast kernel with the same answer
+    th = np.array([0.6, 1.0, 1.9])
+    hb, _ = pb.spm_hrf(th, t_r=0.75, dur=20.0, normalized_hrf=False, p_delay=5.5)
+    for v, t in enumerate(th):
+        h1, _ = pb.spm_hrf(float(t), t_r=0.75, dur=20.0, normalized_hrf=False, p_delay=5.5)
+        assert np.array_equal(hb[v], h1)
+    with pytest.raises(ValueError):
+        pb.spm_hrf(1.0, p_disp=0.0)

@@ -126,12 +126,14 @@ def test_bd_with_reference_theta_solver(golden, tag):
                            trace=trace, **_bd_kwargs(g, tag))
     assert len(d["J"]) == len(g["J_" + tag])
     # the reference's own conditioning is ~3e-8 for a 1e-13 perturbation
-    assert np.max(np.abs(np.array(trace["theta"]) - g["thetas_" + tag])) < 2e-6
-    assert rel(z, g["z_" + tag]) < 1e-5
-    assert rel(h, g["h_" + tag]) < 1e-5
-    assert rel(d["J"], g["J_" + tag]) < 1e-6
-    assert rel(d["r"], g["r_" + tag]) < 1e-6
-    assert rel(d["g"], g["g_" + tag]) < 1e-5
+    # (measured: theta 2.4e-8, z/h 9e-9, J 1.4e-9 at T <= 300; 3.9e-7, 2.8e-7, 5.6e-9 at T = 1200)
+    long = tag.startswith("t1200")
+    assert np.max(np.abs(np.array(trace["theta"]) - g["thetas_" + tag])) < (4e-6 if long else 2.5e-7)
+    assert rel(z, g["z_" + tag]) < (3e-6 if long else 1e-7)
+    assert rel(h, g["h_" + tag]) < (3e-6 if long else 1e-7)
+    assert rel(d["J"], g["J_" + tag]) < (6e-8 if long else 1.5e-8)
+    assert rel(d["r"], g["r_" + tag]) < (6e-8 if long else 1.5e-8)
+    assert rel(d["g"], g["g_" + tag]) < (2.5e-6 if long else 1e-7)
 
 
 def test_theta_step_exact_vs_reference_lbfgsb(golden):
@@ -163,7 +165,96 @@ def test_bd_exact_theta_end_to_end(golden, tag):
     trace = {}
     x, z, w, h, d = orc.bd(g["y_" + tag], float(g["t_r_" + tag]), theta_solver="exact",
                            trace=trace, **_bd_kwargs(g, tag))
-    assert np.max(np.abs(np.array(trace["theta"]) - g["thetas_" + tag])) < 5e-6
-    assert rel(z, g["z_" + tag]) < 2e-5
-    assert rel(h, g["h_" + tag]) < 2e-5
-    assert rel(d["J"], g["J_" + tag]) < 2e-6
+    # measured: theta 5.3e-8, z 6.0e-8, h 6.1e-8, J 3.9e-9
+    assert np.max(np.abs(np.array(trace["theta"]) - g["thetas_" + tag])) < 5e-7
+    assert rel(z, g["z_" + tag]) < 6e-7
+    assert rel(h, g["h_" + tag]) < 6e-7
+    assert rel(d["J"], g["J_" + tag]) < 4e-8
+
+
+# ---- rows A8 / N1 / N2: vectors of the live reference added in round 2 ---------------------------
+def _auto_kwargs(g, tag):
+    return dict(early_stopping=bool(g["early_stopping_" + tag]), tol=float(g["tol_" + tag]),
+                wind=int(g["wind_" + tag]), nb_iter=int(g["nb_iter_" + tag]),
+                nb_sub_iter=int(g["nb_sub_iter_" + tag]))
+
+
+def test_deconv_auto_lambda_vs_reference(golden):
+    """``deconv(lbda=None)`` of the live reference with sigma injected: the oracle's
+    restatement of bold_signal.py:99-214 reproduces it to rounding, outer stop included."""
+    g = golden("deconv_auto")
+    stopped = 0
+    for tag in g["tags"]:
+        kw = _auto_kwargs(g, tag)
+        x, z, w, J, R, G, _ = orc.deconv_auto_lbda(g["y_" + tag], g["h_" + tag], float(g["sigma_" + tag]),
+                                                   x0_power=g["x0_" + tag], **kw)
+        assert len(J) == len(g["J_" + tag]), tag                  # same alpha-window stop iteration
+        stopped += len(J) < kw["nb_iter"]
+        assert np.max(np.abs(w - g["dz_" + tag])) < 1e-18, tag
+        assert np.array_equal(z, g["z_" + tag]), tag
+        assert rel(x, g["x_" + tag]) < 1e-14, tag                  # reference x goes through the FFT
+        for got, key in ((J, "J_"), (R, "R_"), (G, "G_")):
+            assert rel(got, g[key + tag]) < 1e-14, (tag, key)
+    assert stopped >= 2                                            # the alpha window did fire
+
+
+def test_hrf_estim_vs_reference(golden):
+    g = golden("hrf_estim")
+    for tag in g["tags"]:
+        args = (g["z_" + tag], g["y_" + tag], float(g["t_r_" + tag]), float(g["dur_" + tag]))
+        h, J, theta = orc.hrf_estim(*args)                         # same SciPy call as the reference
+        assert rel(h, g["h_" + tag]) < 1e-7 and len(J) == len(g["J_" + tag]), tag
+        assert rel(J, g["J_" + tag]) < 1e-9, tag
+        he, Je, the = orc.hrf_estim_exact(*args)                   # the device algorithm
+        assert abs(the - theta) < 5e-7, tag                        # measured <= 8e-8
+        assert rel(he, g["h_" + tag]) < 2e-6, tag                  # measured <= 2.2e-7
+        assert abs(Je[-1] / g["J_" + tag][-1] - 1) < 1e-12, tag    # flat at the minimum
+
+
+def test_spm_hrf_shape_parameters(golden):
+    g = golden("spm_hrf_params")
+    for i in range(int(g["n"])):
+        kw = {k: float(v) for k, v in g["kw%d" % i]}
+        for norm, key in ((False, "h"), (True, "hn")):
+            h, t = orc.spm_hrf(normalized_hrf=norm, **kw)
+            assert np.array_equal(h, g["%s%d" % (key, i)]) and np.array_equal(t, g["t%d" % i])
+            hc, tc = orc.spm_hrf_general(normalized_hrf=norm, **kw)   # what the device evaluates
+            scale = np.max(np.abs(h)) + 1e-300
+            assert np.max(np.abs(hc - h)) / scale < 1e-12, (i, norm)
+            assert np.max(np.abs(tc - t)) < 1e-9
+
+
+def test_bd_t1200_full_iterations_exact_theta(golden):
+    """cfg4 shape with the reference's nb_iter = 100: theta walks to the lower bound 0.6 and stays."""
+    g = golden("bd_t1200")
+    tag = "t1200_n100"
+    trace = {}
+    x, z, w, h, d = orc.bd(g["y_" + tag], float(g["t_r_" + tag]), theta_solver="exact", trace=trace,
+                           **_bd_kwargs(g, tag))
+    assert np.max(np.abs(np.array(trace["theta"]) - g["thetas_" + tag])) < 1e-5    # measured 1.0e-6
+    assert g["thetas_" + tag][-1] == 0.6 and trace["theta"][-1] == 0.6
+    assert rel(z, g["z_" + tag]) < 3e-7 and rel(x, g["x_" + tag]) < 3e-7           # measured 2.9e-8
+    assert rel(w, g["dz_" + tag]) < 2e-6 and rel(h, g["h_" + tag]) < 1e-12
+    assert rel(d["J"], g["J_" + tag]) < 4e-7 and rel(d["g"], g["g_" + tag]) < 2.5e-6
+
+
+def test_dwt_convention_on_pywavelets_documented_examples():
+    """PyWavelets is absent, so the DWT convention of ``mad_daub_noise_est`` (utils.py:22) is pinned on
+    the Haar examples of PyWavelets' documentation: ``pywt.dwt([1, 2, 3, 4, 5, 6], 'db1')`` gives
+    ``cD = [-0.70710678] * 3``, ``pywt.wavedec(range(1, 9), 'db1', level=2)`` has
+    ``cD1 = [-0.70710678] * 4``; the default mode mirrors ``... x2 x1 | x1 x2 ... xn | xn xn-1 ...`` and
+    a mode-'symmetric' transform of N samples with an F-tap filter has floor((N + F - 1) / 2)
+    coefficients.  (Quoted from the documentation, not generated here.)"""
+    r = np.sqrt(0.5)
+    assert np.allclose(orc.dwt_detail_level1([1, 2, 3, 4, 5, 6], orc._DB1_DEC_HI), [-r] * 3, atol=1e-15)
+    assert np.allclose(orc.dwt_detail_level1(np.arange(1, 9), orc._DB1_DEC_HI), [-r] * 4, atol=1e-15)
+    assert np.allclose(orc.dwt_detail_level1([1, 2, 3], orc._DB1_DEC_HI), [-r, 0.0], atol=1e-15)
+    for T in (10, 11, 300, 301):
+        assert len(orc.db3_detail_level1(np.arange(T, dtype=float))) == (T + 5) // 2
+    # three vanishing moments: a quadratic is annihilated away from the borders
+    t = np.arange(64, dtype=float)
+    cD = orc.db3_detail_level1(3.0 + 0.5 * t - 0.01 * t * t)
+    assert np.max(np.abs(cD[3:-3])) < 1e-10 and np.max(np.abs(cD[:3])) > 1e-3
+    # short series: the reference's level-0 fallback (utils.py:23-24) is the MAD of the series itself
+    x = np.array([0.3, -1.0, 2.0, 0.1, 0.7])
+    assert orc.mad_daub_noise_est(x) == orc.mad(x)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pybold_b200.sharding import bd_sharded, gather_rows, voxel_range
+from pybold_b200.sharding import ALL_OUTPUTS, bd_sharded, gather_outputs, gather_rows, voxel_range
 
 
 def test_voxel_range_partitions_exactly():
@@ -45,6 +45,20 @@ def _worker(rank, world, port, V, T, ret):
         lo, hi = voxel_range(V, rank, world)
         out2 = gather_rows(full[lo:hi].clone(), V)
         ok = ok and torch.equal(out2, full)
+        # every output of the solve, into reused result tensors, twice
+        local = {k: (full[lo:hi, :3] + i if k not in ("theta",) else full[lo:hi, 0] + i)
+                 for i, k in enumerate(ALL_OUTPUTS)}
+        into = None
+        for _ in range(2):
+            into = gather_outputs(local, V, into=into)
+        for i, k in enumerate(ALL_OUTPUTS):
+            want = full[:, :3] + i if k != "theta" else full[:, 0] + i
+            ok = ok and torch.equal(into[k], want)
+        try:
+            gather_rows(full[lo:hi].clone(), V, out=torch.empty(V + 1, T))
+            ok = False
+        except ValueError:
+            pass
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
