@@ -161,6 +161,18 @@ int pb_bd_f64(const double *y, double t_r, double hrf_dur,
               double *out_J, double *out_r, double *out_g, int32_t *out_ntrace,
               int64_t V, int T, int K, pb_stream_t stream);
 
+/* ---- cfg5: regularisation path, `deconv` (fixed lambda, no early stopping, pybold/bold_signal.py:49-97)
+ * for every lambda of lbdas[n_lbda] and every voxel of y[V,T] in one launch -- the lambda grid search of
+ * examples/icassp_2019/validation.py batched over (lambda, voxel).  Problem (l, v) reads row v of y (the
+ * rows are NOT replicated per lambda) and lbdas[l]; h[K] and L[1] are shared.  Outputs are lambda-major:
+ * out_x, out_z, out_dz [n_lbda, V, T], out_J [n_lbda, V, nb_iter] (raw costs), out_niter [n_lbda * V]. */
+int pb_deconv_lbda_path_f32(const float *y, const float *h, const float *L, const float *lbdas, int n_lbda,
+                            int nb_iter, float *out_x, float *out_z, float *out_dz, float *out_J,
+                            int32_t *out_niter, int64_t V, int T, int K, pb_stream_t stream);
+int pb_deconv_lbda_path_f64(const double *y, const double *h, const double *L, const double *lbdas,
+                            int n_lbda, int nb_iter, double *out_x, double *out_z, double *out_dz,
+                            double *out_J, int32_t *out_niter, int64_t V, int T, int K, pb_stream_t stream);
+
 /* ---- A10: the theta step alone / hrf_estim (pybold/bold_signal.py:217-239, :329-334) --
  * theta[v] <- bounded local minimiser of 0.5||y_v - h(theta)*z_v||^2 from theta0;
  * out_h [V,K] = non-normalised taps at the minimiser; out_cost [V] = the cost there. */

@@ -107,38 +107,43 @@ def deconv(y, t_r, hrf, lbda=None, early_stopping=True, tol=1.0e-6,  # noqa
     return (like_input(x, y), like_input(z, y), like_input(dz, y), like_input(Jn, y), None, None)
 
 
-def deconv_lbda_path(y, t_r, hrf, lbdas, nb_iter=200, x0=None, dtype=None, max_problems=1 << 20):
+def deconv_lbda_path(y, t_r, hrf, lbdas, nb_iter=200, x0=None, dtype=None, max_problems=1 << 21):
     """Regularisation path: ``deconv`` (fixed lambda, no early stopping) for every lambda of ``lbdas``
     and every voxel of ``y[V, T]`` -- the grid search of examples/icassp_2019/validation.py batched
     over (lambda, voxel) instead of looping (BASELINE.json configs[4]).
 
     Returns ``(x, z, diff_z, J)`` with a leading lambda axis: ``[n_lbda, V, T]`` and
     ``[n_lbda, V, nb_iter]`` (J normalised by its first entry like ``deconv``).  Every (lambda, voxel)
-    pair is an independent problem of the persistent kernel; at most ``max_problems`` are in flight
-    per launch to bound the temporary copies of ``y``.
+    pair is an independent problem of ONE persistent launch (``pb_deconv_lbda_path_*``) that reads the
+    rows of ``y`` in place -- nothing is replicated per lambda -- and writes straight into the results;
+    more than ``max_problems`` pairs are cut into launches of whole lambdas.
     """
     dtype = pick_dtype(y, hrf, dtype=dtype)
     yb, _ = _as_batch(y, dtype)
+    yb = yb.contiguous()
     V, T = yb.shape
-    hd = to_device(hrf, dtype)
+    hd = to_device(hrf, dtype).reshape(-1).contiguous()
+    K = hd.numel()
     lb = torch.as_tensor(np.asarray(lbdas, dtype=np.float64).reshape(-1)).to(device=yb.device, dtype=dtype)
     n_l = lb.numel()
     if x0 is None:
         x0 = np.random.randn(T)
     est = spectral_radius_est(ConvAndLinear(DiscretInteg(), hd, dim_in=T), (T,), x0=to_device(x0, dtype))
-    lipschitz = 0.9 * est                                         # bold_signal.py:52
+    lipschitz = torch.full((1,), 0.9 * float(est), dtype=dtype, device=yb.device)   # bold_signal.py:52
     outs = [torch.empty((n_l, V, T), dtype=dtype, device=yb.device) for _ in range(3)]
-    Jn = torch.empty((n_l, V, nb_iter), dtype=dtype, device=yb.device)
+    J = torch.empty((n_l, V, nb_iter), dtype=dtype, device=yb.device)
+    n_iter = torch.empty(n_l * V, dtype=torch.int32, device=yb.device)
     per = max(1, min(n_l, max_problems // max(V, 1)))
-    for l0 in range(0, n_l, per):
-        l1 = min(l0 + per, n_l)
-        ytile = yb.unsqueeze(0).expand(l1 - l0, V, T).reshape(-1, T).contiguous()
-        lam = lb[l0:l1].repeat_interleave(V)
-        x, z, dz, J, _ = deconv_batch(ytile, hd, lam, lipschitz, None, False, 1.0e-6, 6, nb_iter)
-        for dst, src in zip(outs, (x, z, dz)):
-            dst[l0:l1] = src.reshape(l1 - l0, V, T)
-        Jn[l0:l1] = (J / (J[:, :1] + 1.0e-30)).reshape(l1 - l0, V, nb_iter)
-    return tuple(like_input(t, y) for t in outs) + (like_input(Jn, y),)
+    with torch.cuda.device(yb.device):
+        for l0 in range(0, n_l, per):
+            l1 = min(l0 + per, n_l)
+            rc = _lib.fn("pb_deconv_lbda_path", dtype)(
+                ptr(yb), ptr(hd), ptr(lipschitz), ptr(lb[l0:l1]), l1 - l0, int(nb_iter),
+                ptr(outs[0][l0:l1]), ptr(outs[1][l0:l1]), ptr(outs[2][l0:l1]), ptr(J[l0:l1]),
+                ptr(n_iter[l0 * V:l1 * V]), V, T, K, stream_ptr())
+            _lib.check(rc, "pb_deconv_lbda_path")
+    J /= (J[:, :, :1] + 1.0e-30)                                   # bold_signal.py:97, in place
+    return tuple(like_input(t, y) for t in outs) + (like_input(J, y),)
 
 
 def bd_alloc(V, T, K, nb_iter, dtype, dev):

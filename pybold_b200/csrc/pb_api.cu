@@ -1,6 +1,7 @@
 // extern "C" boundary of libpybold_b200.so (declared in include/pybold_b200.h).
 // Host-side argument checks, shared-memory sizing, persistent-grid sizing and dispatch between
 // the register-tiled warp kernels (pb_fast.cuh) and the generic kernels (pb_generic.cuh).
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -72,6 +73,21 @@ template <typename K>
 int set_smem(K kernel, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return (int)e;
+}
+
+// Work-queue counters of the early-stopping kernels: the library owns no memory, so the
+// counters live in a small static device array; every launch takes the next slot round-robin and zeroes it
+// on its own stream, which keeps up to 256 launches in flight independent of each other.
+__device__ unsigned int pb_queue_pool[256];
+
+unsigned int *queue_slot() {
+    static std::atomic<unsigned int> next{0};
+    unsigned int *base = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), pb_queue_pool) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return base + (next.fetch_add(1u) & 255u);
 }
 
 int last_error() {
@@ -308,6 +324,7 @@ int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
         return PB_ERR_INVALID_ARG;
     if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
     if (a.V == 0) return PB_OK;
+    if (a.early_stopping && a.wind >= 2) a.queue = queue_slot();
     int rc = pb::fast_deconv_dispatch(a, (cudaStream_t)stream);
     if (rc != pb::FAST_NO_MATCH) return rc;
     DeviceInfo d = device_info();
@@ -336,6 +353,7 @@ int run_bd(pb::BdArgs<real> a, double t_r, double hrf_dur, pb_stream_t stream) {
     if (a.K != a.grid.K) return PB_ERR_INVALID_ARG;
     if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
     if (a.V == 0) return PB_OK;
+    a.queue = queue_slot();     // group / CTA kernels pull their tasks from it (static stride if null)
     int rc = pb::fast_bd_dispatch(a, (cudaStream_t)stream);
     if (rc != pb::FAST_NO_MATCH) return rc;
     DeviceInfo d = device_info();
@@ -578,6 +596,19 @@ int pb_hrf_len_ex(double t_r, double dur, double dt) {
         a.early_stopping = early_stopping; a.wind = wind; a.tol = tol; a.out_x = out_x;                \
         a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J; a.out_niter = out_niter; a.V = V;         \
         a.T = T; a.K = K;                                                                              \
+        return run_deconv<REAL>(a, s);                                                                 \
+    }                                                                                                  \
+    int pb_deconv_lbda_path_##SUF(const REAL *y, const REAL *h, const REAL *L, const REAL *lbdas,      \
+                                  int n_lbda, int nb_iter, REAL *out_x, REAL *out_z, REAL *out_dz,     \
+                                  REAL *out_J, int32_t *out_niter, int64_t V, int T, int K,            \
+                                  pb_stream_t s) {                                                     \
+        if (n_lbda < 0 || V < 0) return PB_ERR_INVALID_ARG;                                            \
+        pb::DeconvArgs<REAL> a;                                                                        \
+        a.y = y; a.h = h; a.h_stride = 0; a.L = L; a.L_stride = 0; a.lbda = lbdas;                     \
+        a.lbda_stride = 0; a.w0 = nullptr; a.nb_iter = nb_iter; a.early_stopping = 0; a.wind = 0;      \
+        a.tol = 0.0; a.out_x = out_x; a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J;             \
+        a.out_niter = out_niter; a.V = (int64_t)n_lbda * V; a.T = T; a.K = K;                          \
+        a.y_mod = V; a.lbda_div = V;                                                                   \
         return run_deconv<REAL>(a, s);                                                                 \
     }                                                                                                  \
     int pb_bd_##SUF(const REAL *y, double t_r, double hrf_dur, const REAL *lbda, int64_t lbda_stride,  \

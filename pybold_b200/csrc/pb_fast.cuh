@@ -267,7 +267,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
     WarpVoxel<real, R, KMAX, CIRC> vx;
     vx.init(lane, T);
     for (int64_t v = (int64_t)blockIdx.x * WARPS + warp; v < p.V; v += (int64_t)gridDim.x * WARPS) {
-        const real *yv = p.y + v * T;
+        const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
         vx.set_dy(yv, T);
 #pragma unroll
@@ -278,7 +278,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
             vx.w[r] = (p.w0 && i < T) ? p.w0[v * T + i] : real(0);
         }
         const double Lc = (double)p.L[v * p.L_stride];
-        const double lam = (double)p.lbda[v * p.lbda_stride];
+        const double lam = p.lam_of(v);
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
         int n_done = 0, ring_pos = 0;

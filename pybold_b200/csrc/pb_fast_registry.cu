@@ -93,7 +93,8 @@ static int bd_dispatch(const BdArgs<real> &a, cudaStream_t s) {
 template <typename real>
 static int deconv_dispatch(const DeconvArgs<real> &a, cudaStream_t s) {
     static const bool no_group = getenv("PB_DISABLE_GROUP") != nullptr;
-    if (!(a.early_stopping && a.wind >= 2) && !no_group) {
+    // early stopping runs on the group layout too when a work-queue counter was provided (a.queue)
+    if ((!(a.early_stopping && a.wind >= 2) || a.queue) && !no_group) {
         int n = 0;
         const FastGEntry<real> *t = fastg_table<real>(&n);
         const FastGEntry<real> *best = nullptr;

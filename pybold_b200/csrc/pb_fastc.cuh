@@ -204,7 +204,9 @@ fast_bdc_kernel(BdArgs<real> p) {
         for (int j = 0; j < KMAX; ++j) h[j] = j < K ? (real)sc.hs[j] : real(0);
     };
 
-    for (int64_t v = blockIdx.x; v < p.V; v += gridDim.x) {
+    // the first voxel of a CTA is static, the following ones come from the work queue when there is one
+    __shared__ unsigned int next_task;
+    for (int64_t v = blockIdx.x; v < p.V;) {
         const real *yv = p.y + v * T;
         real y[R];
 #pragma unroll
@@ -396,8 +398,10 @@ fast_bdc_kernel(BdArgs<real> p) {
         if (tid == 0) {
             p.out_theta[v] = (real)theta;
             p.out_ntrace[v] = ntr;
+            if (p.queue) next_task = atomicAdd(p.queue, 1u);
         }
         __syncthreads();
+        v = p.queue ? (int64_t)gridDim.x + (int64_t)next_task : v + gridDim.x;
     }
 }
 
@@ -427,6 +431,10 @@ int fast_bdc_launch(const BdArgs<real> &a, cudaStream_t stream) {
     if (occ < 1) return FAST_NO_MATCH;
     const int64_t cap = (int64_t)sms * occ;
     const int grid = (int)(a.V < cap ? a.V : cap);
+    if (a.queue) {
+        e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     kern<<<grid, NW * 32, smem, stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;

@@ -139,22 +139,32 @@ struct Seg<float, G> {
 // stores its R values as 16-byte vectors into a per-voxel buffer framed by zero pads and loads the
 // preceding / following samples as vectors (R % 4 == 0).  10 + 10 instead of 38 + 38 instructions
 // per convolution pair at K = 20 and no boundary selects; measured +17 % at T = 600 (pb_fastc.cuh).
+// SMH = 2 ("blocked") does the same for ANY R: every lane owns a 16-byte aligned block of RP >= R floats
+// (RP / 4 odd, so that the 16-byte accesses of a quarter warp fall into distinct banks), stores its R
+// values there (ceil(R / 4) STS.128) and reads the blocks of the lanes before / after it (LDS.128).  The
+// lanes at the ends of a group read a block of zeros instead, picked once per kernel through a pointer:
+// no boundary selects.  K = 20, R = 19: 5 + 5 instead of 19 SHFL + 19 FSEL per exchange.
 #ifdef PB_LEAN_KEEP_TAPS
 constexpr bool kLeanTaps = false;   // experiment: LEAN moves only dy to shared memory
 #else
 constexpr bool kLeanTaps = true;
 #endif
-template <typename real, int R, int KMAX, int G, int TAIL, int J0, bool LEAN = false, bool SMH = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int J0, int LEAN = 0, int SMH = 0>
 struct GroupVoxel {
-    static constexpr bool LT = LEAN && kLeanTaps;
-    static_assert(!SMH || R % 4 == 0, "SMH moves 16-byte vectors");
+    static constexpr bool LT = LEAN == 1 && kLeanTaps;   // LEAN = 2 keeps the taps in registers
+    static_assert(SMH != 1 || R % 4 == 0, "SMH = 1 moves 16-byte vectors of a contiguous copy");
     static constexpr int NH = (KMAX - 1 + 3) / 4;   // vectors per halo
     struct alignas(4 * sizeof(real)) V4 { real t[4]; };
     real *myA;                     // SMH: this lane's R slots in the iterate buffer
     real *myB;                     // SMH: this lane's R slots in the residual buffer
+    static constexpr int RP4 = ((R + 3) / 4) | 1;            // vectors per block (odd)
+    static constexpr int RP = 4 * RP4;                       // SMH = 2: floats per lane block
+    static constexpr int DUP = (KMAX - 1 + R - 1) / R;       // lanes a halo reaches into
+    const real *upsrc[SMH == 2 ? DUP : 1];   // SMH = 2: block of lane q - d in the iterate buffer (or zeros)
+    const real *dnsrc[SMH == 2 ? DUP : 1];   // SMH = 2: block of lane q + d in the residual buffer (or zeros)
     static_assert(G == 8 || G == 16 || G == 32, "group width");
     static_assert(TAIL >= 0 && TAIL <= R, "tail");
-    static_assert(!LEAN || KMAX % 4 == 0, "LEAN fetches taps as 16-byte vectors");
+    static_assert(LEAN != 1 || KMAX % 4 == 0, "LEAN = 1 fetches taps as 16-byte vectors");
     real w[R];                     // iterate (the reference's diff_z)
     real dy[LEAN ? 1 : R];         // y[i] - y[i-1]            (registers unless LEAN)
     real h[LT ? 1 : KMAX];         // taps, zero beyond K       (registers unless LEAN)
@@ -167,6 +177,16 @@ struct GroupVoxel {
         q = lane & (G - 1);
         nvalid = max(0, min(R, T - q * R));
     }
+    // SMH = 2: store the R values as ceil(R / 4) vectors (the pad of the last one is never used)
+    __device__ __forceinline__ void put_block(real *dst, const real (&a)[R]) const {
+#pragma unroll
+        for (int c = 0; c < (R + 3) / 4; ++c) {
+            V4 t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t.t[e] = a[4 * c + e < R ? 4 * c + e : R - 1];
+            reinterpret_cast<V4 *>(dst)[c] = t;
+        }
+    }
     __device__ __forceinline__ void put(real *dst, const real (&a)[R]) const {
 #pragma unroll
         for (int r4 = 0; r4 < R / 4; ++r4) {
@@ -178,7 +198,30 @@ struct GroupVoxel {
     }
     // halo[m-1] = a at voxel index (q R - m), zero before the series starts
     __device__ __forceinline__ void halo_up(const real (&a)[R], real (&halo)[KMAX - 1]) const {
-        if constexpr (SMH) {
+        if constexpr (SMH == 2) {
+            put_block(myA, a);
+            __syncwarp();
+#pragma unroll
+            for (int d = 1; d <= DUP; ++d) {
+                // halo[m - 1], (d - 1) R < m <= min(d R, KMAX - 1), is element d R - m of lane q - d
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int m_hi = d * R < KMAX - 1 ? d * R : KMAX - 1;
+                const int rr_lo = d * R - m_hi;
+#pragma unroll
+                for (int c = rr_lo / 4; c <= (R - 1) / 4; ++c) {
+                    const V4 t = reinterpret_cast<const V4 *>(upsrc[d - 1])[c];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int rr = 4 * c + e;
+                        const int m = d * R - rr;
+                        if (rr >= rr_lo && rr < R) halo[m >= 1 && m <= KMAX - 1 ? m - 1 : 0] = t.t[e];
+                    }
+                }
+            }
+            return;
+        }
+        if constexpr (SMH == 1) {
             put(myA, a);
             __syncwarp();
 #pragma unroll
@@ -200,7 +243,28 @@ struct GroupVoxel {
     }
     // halo[k] = a at voxel index (q R + R + k), zero past the last lane of the group
     __device__ __forceinline__ void halo_down(const real (&a)[R], real (&halo)[KMAX - 1]) const {
-        if constexpr (SMH) {
+        if constexpr (SMH == 2) {
+            put_block(myB, a);
+            __syncwarp();
+#pragma unroll
+            for (int d = 1; d <= DUP; ++d) {
+                // halo[k], (d - 1) R <= k < min(d R, KMAX - 1), is element k - (d - 1) R of lane q + d
+                const int k_hi = d * R < KMAX - 1 ? d * R : KMAX - 1;
+                const int n = k_hi - (d - 1) * R;
+#pragma unroll
+                for (int c = 0; c < (n + 3) / 4; ++c) {
+                    const V4 t = reinterpret_cast<const V4 *>(dnsrc[d - 1])[c];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int rr = 4 * c + e;
+                        const int k = (d - 1) * R + rr;
+                        if (rr < n) halo[k < KMAX - 1 ? k : 0] = t.t[e];
+                    }
+                }
+            }
+            return;
+        }
+        if constexpr (SMH == 1) {
             put(myB, a);
             __syncwarp();
 #pragma unroll
@@ -367,15 +431,19 @@ struct GroupVoxel {
 template <int R, int KMAX, int G>
 __host__ __device__ constexpr int fastg_halo_buf() { return 2 * ((KMAX + 3) & ~3) + G * R; }
 
-template <typename real, int R, int KMAX, int G, bool LEAN, bool SMH = false>
+template <int R>
+__host__ __device__ constexpr int fastg_block_floats() { return 4 * (((R + 3) / 4) | 1); }
+
+template <typename real, int R, int KMAX, int G, int LEAN, int SMH = 0>
 __host__ __device__ constexpr size_t fastg_warp_bytes() {
     return (size_t)(32 / G) * pb_scratch_doubles(KMAX) * sizeof(double) +
            (LEAN ? ((size_t)R * 32 + (size_t)(32 / G) * KMAX) * sizeof(real) : 0) +
-           (SMH ? (size_t)2 * (32 / G) * fastg_halo_buf<R, KMAX, G>() * sizeof(real) : 0);
+           (SMH == 1 ? (size_t)2 * (32 / G) * fastg_halo_buf<R, KMAX, G>() * sizeof(real) : 0) +
+           (SMH == 2 ? (size_t)(2 * 32 + 1) * fastg_block_floats<R>() * sizeof(real) : 0);
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
-          bool SMH = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,
+          int SMH = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_bdg_kernel(BdArgs<real> p) {
     constexpr int VPW = 32 / G;
@@ -398,7 +466,22 @@ fast_bdg_kernel(BdArgs<real> p) {
 
     GroupVoxel<real, R, KMAX, G, TAIL, 1, LEAN, SMH> vx;
     vx.init(lane, T);
-    if (SMH) {
+    if constexpr (SMH == 2) {
+        using GV = GroupVoxel<real, R, KMAX, G, TAIL, 1, LEAN, SMH>;
+        constexpr int RP = GV::RP;
+        real *hb = reinterpret_cast<real *>(wbase + fastg_warp_bytes<real, R, KMAX, G, LEAN, 0>());
+        for (int i = lane; i < (2 * 32 + 1) * RP; i += 32) hb[i] = real(0);
+        real *bufA = hb, *bufB = hb + 32 * RP, *zeros = hb + 64 * RP;
+        vx.myA = bufA + lane * RP;
+        vx.myB = bufB + lane * RP;
+#pragma unroll
+        for (int d = 1; d <= GV::DUP; ++d) {
+            vx.upsrc[d - 1] = vx.q >= d ? bufA + (lane - d) * RP : zeros;
+            vx.dnsrc[d - 1] = vx.q + d < G ? bufB + (lane + d) * RP : zeros;
+        }
+        __syncwarp();
+    }
+    if constexpr (SMH == 1) {
         constexpr int PADH = (KMAX + 3) & ~3, BUFV = fastg_halo_buf<R, KMAX, G>();
         real *hb = reinterpret_cast<real *>(wbase + fastg_warp_bytes<real, R, KMAX, G, LEAN, false>());
         for (int i = lane; i < 2 * VPW * BUFV; i += 32) hb[i] = real(0);   // zero pads (and slots)
@@ -412,8 +495,19 @@ fast_bdg_kernel(BdArgs<real> p) {
         vx.dy_s = lean + VPW * KMAX + lane;
     }
     const int q = vx.q;
-    for (int64_t v0 = ((int64_t)blockIdx.x * WARPS + warp) * VPW; v0 < p.V;
-         v0 += (int64_t)gridDim.x * WARPS * VPW) {
+    // task = VPW consecutive voxels; the first task of a warp is static, the following ones come from the
+    // work queue when there is one (tasks finish at different times as soon as anything else runs on the
+    // GPU, e.g. the NCCL gather of the previous step), else from the usual grid stride
+    const int64_t n_static = (int64_t)gridDim.x * WARPS;
+    for (int64_t task = (int64_t)blockIdx.x * WARPS + warp; task * VPW < p.V;) {
+        const int64_t v0 = task * VPW;
+        if (p.queue) {
+            unsigned int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(p.queue, 1u);
+            task = n_static + (int64_t)__shfl_sync(PB_FULL, nxt, 0);
+        } else {
+            task += n_static;
+        }
         const bool on = v0 + grp < p.V;                 // idle groups replay the last voxel
         const int64_t v = on ? v0 + grp : p.V - 1;
         const real *yv = p.y + v * T;
@@ -572,8 +666,8 @@ int fast_wave_voxels(Kern kern, int threads, size_t smem, int voxels_per_cta) {
     return sms * occ * voxels_per_cta;
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
-          bool SMH = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,
+          int SMH = 0>
 int fast_bdg_wave(int nb_iter) {
     const size_t beta_bytes = ((size_t)nb_iter * sizeof(real) + 15) & ~(size_t)15;
     const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN, SMH>();
@@ -603,7 +697,7 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
          v0 += (int64_t)gridDim.x * WARPS * VPW) {
         const bool on = v0 + grp < p.V;
         const int64_t v = on ? v0 + grp : p.V - 1;
-        const real *yv = p.y + v * T;
+        const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
         vx.set_dy(yv, T);
 #pragma unroll
@@ -614,7 +708,7 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
             vx.w[r] = (p.w0 && i < T) ? p.w0[v * T + i] : real(0);
         }
         const double Lc = (double)p.L[v * p.L_stride];
-        const double lam = (double)p.lbda[v * p.lbda_stride];
+        const double lam = p.lam_of(v);
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
         const bool writer = on && q == 0;
@@ -652,9 +746,203 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// deconv with EARLY STOPPING (the reference's default call, pybold/bold_signal.py:13, :82-95; Q5), group
+// layout.  Iteration counts differ from voxel to voxel, so
+//  * every group of a warp runs its own voxel at its own iteration k (own momentum weight, own ring
+//    position, own stop test); a group whose voxel stops -- or reaches nb_iter -- stores it and
+//  * pulls the next voxel from an atomic work queue (p.queue) while its neighbour group carries on.
+// The warp executes one common instruction stream (the iteration body); only the per-voxel prologue /
+// epilogue is predicated.  Results cannot depend on which group solves a voxel: the arithmetic of a
+// voxel only involves its own G lanes, in the same lane order.
+// Ring of the past u's (Q5 window): [slot][lane][RP] in shared memory, every lane reads and writes its
+// own 16-byte aligned block with vector accesses (RP / 4 odd: conflict free).
+// ------------------------------------------------------------------------------------------------
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
+    using GV = GroupVoxel<real, R, KMAX, G, TAIL, 0>;
+    using V4 = typename GV::V4;
+    constexpr int RP = GV::RP, NV = (R + 3) / 4;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    real *beta = reinterpret_cast<real *>(smem);
+    const size_t beta_bytes = ((size_t)p.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    fill_momentum_table(beta, p.nb_iter);
+    real *ring = reinterpret_cast<real *>(smem + beta_bytes) + ((size_t)warp * ring_rows * 32 + lane) * RP;
+    const int T = p.T, K = p.K;
+    const int sub = p.wind / 2, nring = p.wind - 1;
+    const real inv_old = real(1) / real(p.wind - sub), inv_new = real(1) / real(sub);
+    GV vx;
+    vx.init(lane, T);
+    const int q = vx.q;
+#pragma unroll
+    for (int r = 0; r < R; ++r) vx.w[r] = vx.dy[r] = real(0);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) vx.h[j] = real(0);
+    // per-group state (identical in the G lanes of a group)
+    int64_t v = 0;
+    int k = 0, ring_pos = 0;
+    bool active = false, want = true;
+    double lam = 0.0;
+    real step = 0, th = 0;
+    for (;;) {
+        if (__any_sync(PB_FULL, want)) {
+            unsigned int idx = 0xffffffffu;
+            if (want && q == 0) idx = atomicAdd(p.queue, 1u);
+            idx = __shfl_sync(PB_FULL, idx, 0, G);
+            if (want) {
+                want = false;
+                active = (int64_t)idx < p.V;
+                if (active) {
+                    v = idx;
+                    const real *hv = p.h + v * p.h_stride;
+                    vx.set_dy(p.y_row(v), T);
+#pragma unroll
+                    for (int j = 0; j < KMAX; ++j) vx.h[j] = j < K ? hv[j] : real(0);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const int i = q * R + r;
+                        vx.w[r] = (p.w0 && i < T) ? p.w0[v * T + i] : real(0);
+                    }
+                    const double Lc = (double)p.L[v * p.L_stride];
+                    lam = p.lam_of(v);
+                    step = (real)(1.0 / Lc);
+                    th = (real)(lam / Lc);
+                    k = 0;
+                    ring_pos = 0;
+                }
+            }
+        }
+        if (!__any_sync(PB_FULL, active)) break;
+        const bool writer = active && q == 0;
+        real *Jv = p.out_J + v * (int64_t)p.nb_iter;
+        real res[R];
+        vx.forward(res);
+        {   // cost of the previous iterate: its residual has just been formed
+            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
+                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            if (writer && k > 0) Jv[k - 1] = (real)J;
+        }
+        real g[R], u[R];
+        vx.adjoint(res, g);
+        {
+            const real ob = real(1) + beta[k];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                u[r] = fma(-step, g[r], vx.w[r]);
+                const real cl = fmin(fmax(u[r], -th), th);
+                vx.w[r] = fma(-ob, cl, u[r]);
+            }
+        }
+        {   // u_k into the ring slot k % nring
+            real *slot = ring + (size_t)ring_pos * 32 * RP;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                V4 t;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t.t[e] = u[4 * c + e < R ? 4 * c + e : R - 1];
+                reinterpret_cast<V4 *>(slot)[c] = t;
+            }
+        }
+        // xx = [u_{k-wind+2}, ..., u_k, w_k]; old = mean(first wind - sub), new = mean(last sub)
+        bool stop = false;
+        if (__any_sync(PB_FULL, active && k > p.wind)) {
+            real so[R], sn[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                so[r] = 0;
+                sn[r] = vx.w[r];
+            }
+            int pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;       // oldest u of this group's window
+            for (int m = 0; m < p.wind - 1; ++m) {
+                const real *slot = ring + (size_t)pos * 32 * RP;
+                pos = pos + 1 == nring ? 0 : pos + 1;
+                const bool is_old = m < p.wind - sub;
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+                    const V4 t = reinterpret_cast<const V4 *>(slot)[c];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (4 * c + e < R) {
+                            if (is_old) so[4 * c + e < R ? 4 * c + e : 0] += t.t[e];
+                            else sn[4 * c + e < R ? 4 * c + e : 0] += t.t[e];
+                        }
+                    }
+                }
+            }
+            real qn = 0, qd = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const real mo = so[r] * inv_old, mn = sn[r] * inv_new;
+                qn = fma(mn - mo, mn - mo, qn);
+                qd = fma(mn, mn, qd);
+            }
+            const double pn = (double)Seg<real, G>::sum(qn);
+            const double pd = (double)Seg<real, G>::sum(qd);
+            stop = k > p.wind && sqrt(pn) / (sqrt(pd) + 1.0e-10) < p.tol;
+        }
+        const bool fin = active && (stop || k + 1 == p.nb_iter);
+        if (__any_sync(PB_FULL, fin)) {
+            // epilogue of the finishing group(s); the other group's iterate is not touched
+            vx.forward(res);
+            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
+                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            real z[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
+            vx.scan_fwd(z);
+            if (fin) {
+                if (q == 0) {
+                    Jv[k] = (real)J;
+                    p.out_niter[v] = k + 1;
+                }
+                real y[R];
+                vx.load_y(p.y_row(v), T, y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[r] += res[r];          // x = (A w - y) + y
+                vx.store(p.out_x + v * T, y, T, true);
+                vx.store(p.out_z + v * T, z, T, true);
+                vx.store(p.out_dz + v * T, vx.w, T, true);
+                want = true;
+                active = false;
+            }
+        }
+        // groups without a voxel keep iterating on stale registers; keep their indices in range
+        k = k + 1 < p.nb_iter ? k + 1 : p.nb_iter - 1;
+        ring_pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;
+    }
+}
+
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
 int fast_deconvg_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
     constexpr int VPW = 32 / G;
+    if (a.early_stopping && a.wind >= 2) {
+        if (!a.queue) return FAST_NO_MATCH;
+        const int ring_rows = a.wind - 1;
+        const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+        const size_t smem_es = beta_bytes + (size_t)WARPS * ring_rows * 32 * fastg_block_floats<R>() * sizeof(real);
+        auto kes = fast_deconvg_es_kernel<real, R, KMAX, G, TAIL, WARPS, MINB>;
+        int dev = 0, sms = 0, occ = 0, max_smem = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (smem_es > (size_t)max_smem) return FAST_NO_MATCH;
+        e = cudaFuncSetAttribute(kes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_es);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kes, WARPS * 32, smem_es);
+        if (e != cudaSuccess) return (int)e;
+        if (occ < 1) return FAST_NO_MATCH;
+        e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return (int)e;
+        const int64_t per_cta = (int64_t)WARPS * VPW;
+        const int64_t need = (a.V + per_cta - 1) / per_cta;
+        const int64_t cap = (int64_t)sms * occ;
+        kes<<<(int)(need < cap ? need : cap), WARPS * 32, smem_es, stream>>>(a, ring_rows);
+        e = cudaGetLastError();
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     const size_t smem = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     auto kern = fast_deconvg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB>;
     int dev = 0, sms = 0, occ = 0;
@@ -680,8 +968,8 @@ bool fastg_shape_ok(int T, int K) {
     return K <= KMAX && T <= G * R && (G == 8 && TAIL == R ? 2 * T > G * R : G * R - T <= TAIL) && T >= 1;
 }
 
-template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false,
-          bool SMH = false>
+template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,
+          int SMH = 0>
 int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
     constexpr int VPW = 32 / G;
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
@@ -703,6 +991,10 @@ int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
     const int64_t need = (a.V + per_cta - 1) / per_cta;
     const int64_t cap = (int64_t)sms * occ;
     const int grid = (int)(need < cap ? need : cap);
+    if (a.queue) {
+        e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned int), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     kern<<<grid, WARPS * 32, smem, stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;

@@ -209,6 +209,16 @@ struct DeconvArgs {
     int32_t *out_niter;
     int64_t V;
     int T, K;
+    // regularisation path (cfg5): problem p = l * y_mod + v solves voxel v with lambda l.  y_mod > 0 makes
+    // the problems share the y rows (row p % y_mod) instead of a replicated copy, lbda_div > 0 takes
+    // lbda[p / lbda_div].  Both 0: one y row and one lbda (element stride lbda_stride) per problem.
+    int64_t y_mod = 0, lbda_div = 0;
+    // early-stopping group kernel: device counter (zeroed on the launch stream) the groups pull voxels from
+    unsigned int *queue = nullptr;
+    __device__ __forceinline__ const real *y_row(int64_t v) const { return y + (y_mod ? v % y_mod : v) * T; }
+    __device__ __forceinline__ double lam_of(int64_t v) const {
+        return (double)lbda[lbda_div ? v / lbda_div : v * lbda_stride];
+    }
 };
 
 template <typename real>
@@ -226,7 +236,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
     const int sub = p.wind / 2, nring = p.wind - 1;
 
     for (int64_t v = (int64_t)blockIdx.x * nwarp + warp; v < p.V; v += (int64_t)gridDim.x * nwarp) {
-        const real *yv = p.y + v * T;
+        const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
         for (int i = lane; i < T; i += 32) {
             g.ys[i] = yv[i];
@@ -235,7 +245,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
         for (int a = lane; a < K; a += 32) g.hr[a] = hv[a];
         __syncwarp();
         const double Lc = (double)p.L[v * p.L_stride];
-        const double lam = (double)p.lbda[v * p.lbda_stride];
+        const double lam = p.lam_of(v);
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
         int n_done = 0;
@@ -305,6 +315,9 @@ struct BdArgs {
     int32_t *out_ntrace;
     int64_t V;
     int T, K;
+    // optional work-queue counter (zeroed on the launch stream): after its first, statically assigned task a
+    // warp / CTA pulls the next one from it instead of striding through the batch.  Same results either way.
+    unsigned int *queue = nullptr;
 };
 
 // Q7: outer early stop of bd on the (signed) relative change of windowed means of J.

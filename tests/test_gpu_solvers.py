@@ -72,6 +72,43 @@ def test_deconv_batch_vs_oracle(dt, tol):
         assert rel(J[v], Jo) < tol
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_deconv_early_stopping_group_kernel_with_work_queue(dt):
+    """The reference's default call (early_stopping=True, bold_signal.py:13) runs on the group layout:
+    every voxel stops at its own iteration, groups pull voxels from an atomic queue.  (a) iteration
+    counts and results equal the oracle's (FP64); (b) a voxel's result does not depend on where it sits
+    in the batch, i.e. on which group pulled it and when: permuted batch == permuted results, bit for
+    bit; (c) it equals the one-voxel call."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    V, T = 333, 300
+    assert _lib.lib.pb_solver_variant(T, 20, int(dt == np.float64)) // 1000000 == 16
+    y = gen_voxels(V, T, 1.0, 20.0, seed0=1500)
+    y *= np.linspace(0.2, 3.0, V)[:, None]           # spread the stopping iterations
+    h, _ = orc.spm_hrf(1.0, 1.0, 20.0, True)
+    x0 = np.random.RandomState(0).randn(T)
+    kw = dict(lbda=1.0, early_stopping=True, tol=5e-3, wind=6, nb_iter=400, x0=x0.astype(dt))
+    x, z, dz, J, _, _ = pb.deconv(y.astype(dt), 1.0, h.astype(dt), **kw)
+    n_it = np.sum(~np.isnan(J), axis=1)
+    assert n_it.min() < n_it.max() and n_it.min() > 6 and n_it.max() <= 400
+    perm = np.random.RandomState(1).permutation(V)
+    xp, zp, dzp, Jp, _, _ = pb.deconv(y[perm].astype(dt), 1.0, h.astype(dt), **kw)
+    assert np.array_equal(zp, z[perm]) and np.array_equal(dzp, dz[perm]) and np.array_equal(xp, x[perm])
+    assert np.array_equal(np.isnan(Jp), np.isnan(J[perm]))
+    assert np.array_equal(np.nan_to_num(Jp), np.nan_to_num(J[perm]))
+    for v in (0, 7, V - 1):
+        x1, z1, dz1, J1, _, _ = pb.deconv(y[v].astype(dt), 1.0, h.astype(dt), **kw)
+        assert len(J1) == n_it[v] and np.array_equal(z1, z[v]) and np.array_equal(J1, J[v, :n_it[v]])
+    if dt == np.float64:
+        Lc = 0.9 * orc.spectral_radius_est(orc.HrfIntegOperator(h, T), x0)
+        for v in range(0, V, 37):
+            xo, zo, wo, Jo, n_o = orc.deconv_fixed_lbda(y[v], h, 1.0, lipschitz=Lc, early_stopping=True,
+                                                        tol=5e-3, wind=6, nb_iter=400)
+            assert n_o == n_it[v], v
+            assert rel(dz[v], wo) < 1e-9 and rel(x[v], xo) < 1e-9
+            assert rel(J[v, :n_o], np.asarray(Jo)) < 1e-9
+
+
 def test_deconv_ragged_and_edge_shapes():
     import pybold_b200 as pb
     rng = np.random.RandomState(3)

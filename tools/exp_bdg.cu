@@ -98,7 +98,7 @@ void run32(const char *name, Bufs &b, int nb_iter, bool is_ref) {
     const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * pb_scratch_doubles(KMAX) * 8;
     time_it(name, b, [&] { return fast_bd_launch<float, R, KMAX, CIRC, WARPS, MINB>(b.a, 0); }, kern, WARPS, smem, nb_iter, is_ref);
 }
-template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB, bool LEAN = false, bool SMH = false>
+template <int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0, int SMH = 0>
 void rung(const char *name, Bufs &b, int nb_iter, bool is_ref = false) {
     auto kern = fast_bdg_kernel<float, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>;
     const size_t smem = (((size_t)nb_iter * 4 + 15) & ~(size_t)15) + (size_t)WARPS * fastg_warp_bytes<float, R, KMAX, G, LEAN, SMH>();
@@ -117,6 +117,16 @@ int main(int argc, char **argv) {
     if (set == 0) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
+        b.free_all();
+    } else if (set == 4) {      // round 2: blocked shared-memory halo exchange, occupancy
+        Bufs b; b.alloc(42624, 300, 1.0, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3 (r01)", b, 100, true);
+        rung<19, 20, 16, 8, 4, 3, 0, 2>("G16 R19 SMH2 M3", b, 100);
+        rung<19, 20, 16, 8, 4, 4, 0, 2>("G16 R19 SMH2 M4", b, 100);
+        rung<19, 20, 16, 8, 4, 4, 2, 2>("G16 R19 SMH2 LEAN2 M4", b, 100);
+        rung<19, 20, 16, 8, 4, 3, 2, 2>("G16 R19 SMH2 LEAN2 M3", b, 100);
+        rung<20, 20, 16, 8, 4, 3, 0, 2>("G16 R20 SMH2 M3", b, 100);
+        rung<20, 20, 16, 8, 4, 4, 1, 2>("G16 R20 SMH2 LEAN1 M4", b, 100);
         b.free_all();
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);

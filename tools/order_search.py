@@ -21,6 +21,8 @@ from rf_model import score  # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAMILY = {
     "group": ("pb_fastg.cuh", "fast_bdg_launch<float, 19, 20, 16, 8, 4, 3>", "BdArgs", "fast_bdg_kernel", "PB_"),
+    "group_smh2": ("pb_fastg.cuh", "fast_bdg_launch<float, 19, 20, 16, 8, 4, 3, 0, 2>", "BdArgs", "fast_bdg_kernel", "PB_"),
+    "group_smh2_m4": ("pb_fastg.cuh", "fast_bdg_launch<float, 19, 20, 16, 8, 4, 4, 0, 2>", "BdArgs", "fast_bdg_kernel", "PB_"),
     "group_deconv": ("pb_fastg.cuh", "fast_deconvg_launch<float, 19, 20, 16, 8, 4, 3>", "DeconvArgs", "fast_deconvg_kernel", "PB_"),
     "cta": ("pb_fastc.cuh", "fast_bdc_launch<float, 20, 28, 2, 6>", "BdArgs", "fast_bdc_kernel", "PB_C_"),
     "warp": ("pb_fast.cuh", "fast_deconv_launch<float, 20, 20, true, 4, 3>", "DeconvArgs", "fast_deconv_kernel", "PB_W_"),
