@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/pybold_b200.h"
 #include "pb_fast_registry.h"
@@ -12,6 +13,7 @@
 #include "pb_ops_rows.cuh"
 #include "pb_noise.cuh"
 #include "pb_synth.cuh"
+#include "pb_transpose_tma.cuh"
 
 #define PB_VERSION 100   /* 0.1.0 */
 #define PB_MAX_T 4096
@@ -298,6 +300,15 @@ template <typename real>
 int run_transpose(const real *in, real *out, int64_t rows, int64_t cols, pb_stream_t stream) {
     if (rows == 0 || cols == 0) return PB_OK;
     if (!in || !out || rows < 0 || cols < 0 || in == out) return PB_ERR_INVALID_ARG;
+    // TMA tile mover when pointers and row pitches are 16-byte aligned (pb_transpose_tma.cuh);
+    // PB_TRANSPOSE_NO_TMA=1 keeps the plain-load kernel for A/B timing
+    static const bool no_tma = getenv("PB_TRANSPOSE_NO_TMA") != nullptr;
+    if (!no_tma) {
+        DeviceInfo d = device_info();
+        if (d.err) return d.err;
+        const int rc = pb::transpose_tma_launch<real>(in, out, rows, cols, d.sm_count, (cudaStream_t)stream);
+        if (rc != -1000) return rc == 0 ? PB_OK : rc;
+    }
     const int64_t gx = (cols + 63) / 64, gy = (rows + 63) / 64;
     if (gy > 65535 || gx > 2147483647LL) return PB_ERR_UNSUPPORTED;
     pb::transpose_kernel<real><<<dim3((unsigned)gx, (unsigned)gy), dim3(32, 8), 0, (cudaStream_t)stream>>>(

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
+
+torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import pybold_oracle as orc  # noqa: E402
@@ -137,6 +139,32 @@ def test_layout_adapter_roundtrip_and_ragged_tiles():
         assert np.array_equal(back.cpu().numpy(), a)
     with pytest.raises(ValueError):
         voxels_from_timeseries(np.zeros(5))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_layout_adapter_tma_tiles(dt):
+    """The TMA tile mover (csrc/pb_transpose_tma.cuh) serves 16-byte aligned row pitches: full tiles,
+    edge boxes clipped by the tensor maps, more tiles than CTAs x stages (mbarrier phases wrap), matrices
+    smaller than one box, and a misaligned base pointer falling back to the plain kernel -- all exact."""
+    from pybold_b200.io import timeseries_from_voxels, voxels_from_timeseries
+    rng = np.random.RandomState(3)
+    q = 4 if dt is np.float32 else 2
+    for (T, V) in [(64, 64), (128, 256), (4 * q, 8 * q), (300, 1000), (1200, 4096), (68, 10 ** 5), (2048, 3000),
+                   (36, 60)]:
+        assert T % q == 0 and V % q == 0
+        a = torch.as_tensor(rng.randn(T, V).astype(dt), device="cuda")
+        vt = voxels_from_timeseries(a)
+        assert vt.shape == (V, T) and torch.equal(vt, a.t().contiguous()), (T, V)
+        assert torch.equal(timeseries_from_voxels(vt), a), (T, V)
+    # same data at a base address that is only element-aligned: plain-load kernel, same answer
+    buf = torch.as_tensor(rng.randn(300 * 1000 + 1).astype(dt), device="cuda")
+    a = buf[1:].reshape(300, 1000)
+    assert a.data_ptr() % 16 != 0
+    from pybold_b200 import _lib
+    out = torch.empty((1000, 300), dtype=a.dtype, device="cuda")
+    assert _lib.fn("pb_transpose", a.dtype)(a.data_ptr(), out.data_ptr(), 300, 1000, 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, a.t().contiguous())
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
