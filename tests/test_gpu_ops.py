@@ -4,8 +4,6 @@ import numpy as np
 import pytest
 
 torch = pytest.importorskip("torch")
-
-torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 from oracle import pybold_oracle as orc  # noqa: E402
