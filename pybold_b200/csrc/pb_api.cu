@@ -163,12 +163,49 @@ int pick_rows_conv_nch(const DeviceInfo &d, const float *h, int64_t h_stride, co
     return launch_rows_conv<OP, KMAX, 10>(d, h, h_stride, x, out, V, T, K, stream);
 }
 
+template <int OP, int KMAX, int NCH>
+int launch_rows_conv8(const DeviceInfo &d, const float *h, int64_t h_stride, const float *x, float *out,
+                      int64_t V, int T, int K, pb_stream_t stream) {
+    using L = pb::RowsConv8Layout<KMAX, NCH>;
+    const int warps = 8;
+    const size_t smem = (size_t)warps * L::WARP_BYTES;
+    auto kern = pb::rows_conv8_kernel<OP, KMAX, NCH>;
+    int e = set_smem(kern, smem);
+    if (e) return e;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return NO_FAST_OP;
+    }
+    const int64_t need = (V + warps - 1) / warps;
+    const int64_t cap = (int64_t)d.sm_count * occ;
+    kern<<<(int)(need < cap ? need : cap), warps * 32, smem, (cudaStream_t)stream>>>(h, h_stride, x, out, V, T, K);
+    return last_error();
+}
+
+template <int OP, int KMAX>
+int pick_rows_conv8_nch(const DeviceInfo &d, const float *h, int64_t h_stride, const float *x, float *out,
+                        int64_t V, int T, int K, pb_stream_t stream) {
+    if (T <= 512) return launch_rows_conv8<OP, KMAX, 2>(d, h, h_stride, x, out, V, T, K, stream);
+    return launch_rows_conv8<OP, KMAX, 5>(d, h, h_stride, x, out, V, T, K, stream);
+}
+
+inline bool aligned32(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
 template <int OP>
 int run_rows_conv(const float *h, int64_t h_stride, const float *x, float *out, int64_t V, int T, int K,
                   pb_stream_t stream) {
     if (T % 4 != 0 || !aligned16(x) || !aligned16(out) || T > 1280 || K > 32) return NO_FAST_OP;
     DeviceInfo d = device_info();
     if (d.err) return d.err;
+    // 32-byte rows: eight samples per lane (half the shared-memory window traffic); PB_ROWS_CONV4=1 keeps
+    // the four-sample kernel for A/B timing
+    static const bool conv4 = getenv("PB_ROWS_CONV4") != nullptr;
+    if (!conv4 && T % 8 == 0 && aligned32(x) && aligned32(out)) {
+        if (K <= 20) return pick_rows_conv8_nch<OP, 20>(d, h, h_stride, x, out, V, T, K, stream);
+        if (K <= 28) return pick_rows_conv8_nch<OP, 28>(d, h, h_stride, x, out, V, T, K, stream);
+        return pick_rows_conv8_nch<OP, 32>(d, h, h_stride, x, out, V, T, K, stream);
+    }
     if (K <= 20) return pick_rows_conv_nch<OP, 20>(d, h, h_stride, x, out, V, T, K, stream);
     if (K <= 28) return pick_rows_conv_nch<OP, 28>(d, h, h_stride, x, out, V, T, K, stream);
     return pick_rows_conv_nch<OP, 32>(d, h, h_stride, x, out, V, T, K, stream);
@@ -364,7 +401,8 @@ int run_bd(pb::BdArgs<real> a, double t_r, double hrf_dur, pb_stream_t stream) {
     if (a.K != a.grid.K) return PB_ERR_INVALID_ARG;
     if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
     if (a.V == 0) return PB_OK;
-    a.queue = queue_slot();     // group / CTA kernels pull their tasks from it (static stride if null)
+    // group / CTA kernels pull their tasks from it (static stride if null; PB_NO_QUEUE=1: developer A/B switch)
+    a.queue = getenv("PB_NO_QUEUE") ? nullptr : queue_slot();
     int rc = pb::fast_bd_dispatch(a, (cudaStream_t)stream);
     if (rc != pb::FAST_NO_MATCH) return rc;
     DeviceInfo d = device_info();

@@ -783,7 +783,7 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
     // per-group state (identical in the G lanes of a group)
     int64_t v = 0;
     int k = 0, ring_pos = 0;
-    bool active = false, want = true;
+    bool active = false, want = true, closing = false;
     double lam = 0.0;
     real step = 0, th = 0;
     for (;;) {
@@ -815,14 +815,37 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
             }
         }
         if (!__any_sync(PB_FULL, active)) break;
-        const bool writer = active && q == 0;
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
         real res[R];
         vx.forward(res);
-        {   // cost of the previous iterate: its residual has just been formed
+        {   // cost of the previous iterate: its residual has just been formed.  For a closing voxel k is the
+            // number of iterations done and this is its last cost.
             const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
                              lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-            if (writer && k > 0) Jv[k - 1] = (real)J;
+            if (active && q == 0 && k > 0) Jv[k - 1] = (real)J;
+        }
+        if (__any_sync(PB_FULL, closing)) {
+            // A voxel that stopped in the previous turn: the residual of its final iterate is the one just
+            // formed.  Store it and hand the group back to the queue; the neighbour group loses this
+            // turn's forward pass (its iterate is untouched), once per voxel.
+            real z[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
+            vx.scan_fwd(z);
+            if (closing) {
+                if (q == 0) p.out_niter[v] = k;
+                real y[R];
+                vx.load_y(p.y_row(v), T, y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[r] += res[r];          // x = (A w - y) + y
+                vx.store(p.out_x + v * T, y, T, true);
+                vx.store(p.out_z + v * T, z, T, true);
+                vx.store(p.out_dz + v * T, vx.w, T, true);
+                closing = false;
+                active = false;
+                want = true;
+            }
+            continue;
         }
         real g[R], u[R];
         vx.adjoint(res, g);
@@ -855,22 +878,19 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
                 sn[r] = vx.w[r];
             }
             int pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;       // oldest u of this group's window
-            for (int m = 0; m < p.wind - 1; ++m) {
+            auto add_slot = [&](real (&acc)[R]) {
                 const real *slot = ring + (size_t)pos * 32 * RP;
                 pos = pos + 1 == nring ? 0 : pos + 1;
-                const bool is_old = m < p.wind - sub;
 #pragma unroll
                 for (int c = 0; c < NV; ++c) {
                     const V4 t = reinterpret_cast<const V4 *>(slot)[c];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (4 * c + e < R) {
-                            if (is_old) so[4 * c + e < R ? 4 * c + e : 0] += t.t[e];
-                            else sn[4 * c + e < R ? 4 * c + e : 0] += t.t[e];
-                        }
-                    }
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * c + e < R) acc[4 * c + e < R ? 4 * c + e : 0] += t.t[e];
                 }
-            }
+            };
+            for (int m = 0; m < p.wind - sub; ++m) add_slot(so);
+            for (int m = p.wind - sub; m < p.wind - 1; ++m) add_slot(sn);
             real qn = 0, qd = 0;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -882,34 +902,9 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
             const double pd = (double)Seg<real, G>::sum(qd);
             stop = k > p.wind && sqrt(pn) / (sqrt(pd) + 1.0e-10) < p.tol;
         }
-        const bool fin = active && (stop || k + 1 == p.nb_iter);
-        if (__any_sync(PB_FULL, fin)) {
-            // epilogue of the finishing group(s); the other group's iterate is not touched
-            vx.forward(res);
-            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
-                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-            real z[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
-            vx.scan_fwd(z);
-            if (fin) {
-                if (q == 0) {
-                    Jv[k] = (real)J;
-                    p.out_niter[v] = k + 1;
-                }
-                real y[R];
-                vx.load_y(p.y_row(v), T, y);
-#pragma unroll
-                for (int r = 0; r < R; ++r) y[r] += res[r];          // x = (A w - y) + y
-                vx.store(p.out_x + v * T, y, T, true);
-                vx.store(p.out_z + v * T, z, T, true);
-                vx.store(p.out_dz + v * T, vx.w, T, true);
-                want = true;
-                active = false;
-            }
-        }
-        // groups without a voxel keep iterating on stale registers; keep their indices in range
-        k = k + 1 < p.nb_iter ? k + 1 : p.nb_iter - 1;
+        closing = active && (stop || k + 1 == p.nb_iter);
+        // k = iterations done; groups without a voxel iterate on stale registers, keep their indices in range
+        k = k + 1 < p.nb_iter || closing ? k + 1 : p.nb_iter - 1;
         ring_pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;
     }
 }

@@ -192,4 +192,169 @@ rows_conv_kernel(const real *__restrict__ h, int64_t h_stride, const real *__res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Round 2: the same four operators with EIGHT consecutive samples per lane (float only).
+//  * rows move as 32-byte vectors (ld.global.v8 / st.global.v8, sm_100: LDG.E.256 / STG.E.256): a warp
+//    request still covers 1 KB of contiguous row;
+//  * every window vector (16 bytes) read from shared memory now feeds 8 outputs instead of 4:
+//    (K + 10) / 4 window loads per 8 outputs instead of 2 (K + 6) / 4 -- K = 28: 10 against 16 -- which
+//    is what bounded the 4-sample kernel (70 % of the shared-memory wavefront peak at 0.71 of HBM);
+//  * the shared copy of the row is skewed: one unused 16-byte slot after every 8 vectors, so that the
+//    32-byte lane stride of these loads / stores touches every bank once per quarter warp (without the
+//    skew they are 2-way conflicts, the variant round 1 measured and rejected).
+// Rows must start on 32-byte boundaries (T % 8 == 0), T <= 256 NCH, K <= KMAX <= 32.
+// ------------------------------------------------------------------------------------------------
+struct alignas(32) Vec32f {
+    float t[8];
+};
+__device__ __forceinline__ Vec32f ldg256(const float *p) {
+    Vec32f v;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v.t[0]), "=f"(v.t[1]), "=f"(v.t[2]), "=f"(v.t[3]), "=f"(v.t[4]), "=f"(v.t[5]), "=f"(v.t[6]),
+                   "=f"(v.t[7])
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg256(float *p, const Vec32f &v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v.t[0]), "f"(v.t[1]),
+                 "f"(v.t[2]), "f"(v.t[3]), "f"(v.t[4]), "f"(v.t[5]), "f"(v.t[6]), "f"(v.t[7])
+                 : "memory");
+}
+
+template <int KMAX, int NCH>
+struct RowsConv8Layout {
+    static constexpr int NPV = (KMAX - 1 + 3) / 4;                  // vectors the taps reach beyond an output pair
+    static constexpr int FRAME = 8;                                 // zero vectors on each side (>= NPV)
+    static constexpr int NV = 64 * NCH;                             // data vectors (16 bytes each)
+    static constexpr int SLOTS = ((NV + 2 * FRAME) / 8) * 9;        // with the skew slots
+    static constexpr size_t WARP_BYTES = (size_t)SLOTS * 16 + (size_t)KMAX * sizeof(float);
+    static_assert(NPV <= FRAME, "taps reach beyond the zero frame");
+    // slot of logical vector v (v = -FRAME .. NV + FRAME - 1)
+    __host__ __device__ static constexpr int slot(int v) { return (v + FRAME) + (v + FRAME) / 8; }
+};
+
+template <int OP, int KMAX, int NCH>
+__global__ void __launch_bounds__(256, 2)
+rows_conv8_kernel(const float *__restrict__ h, int64_t h_stride, const float *__restrict__ x, float *out,
+                  int64_t V, int T, int K) {
+    using L = RowsConv8Layout<KMAX, NCH>;
+    constexpr bool ADJ = OP == OP_CONV_ADJ || OP == OP_HRFINTEG_ADJ;
+    constexpr int NPV = L::NPV;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    Vec16<float> *row = reinterpret_cast<Vec16<float> *>(smem + (size_t)warp * L::WARP_BYTES);
+    float *hs = reinterpret_cast<float *>(row + L::SLOTS);
+    for (int i = lane; i < L::SLOTS; i += 32)
+        row[i] = Vec16<float>{{0.f, 0.f, 0.f, 0.f}};              // zero frames (and everything else once)
+    const int n8 = T / 8;
+    float taps[KMAX];
+    bool have_taps = false;
+    for (int64_t v = (int64_t)blockIdx.x * nw + warp; v < V; v += (int64_t)gridDim.x * nw) {
+        Vec32f d[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {                             // the whole row in flight
+            const int i = c * 32 + lane;
+            if (i < n8) {
+                d[c] = ldg256(x + v * T + 8 * (int64_t)i);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[c].t[e] = 0.f;
+            }
+        }
+        if (h_stride != 0 || !have_taps) {
+            __syncwarp();
+            for (int a = lane; a < KMAX; a += 32) hs[a] = a < K ? h[v * h_stride + a] : 0.f;
+        }
+        if (OP == OP_HRFINTEG) {                                    // cumsum first (pybold/linear.py:86)
+            float carry = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                for (int e = 1; e < 8; ++e) d[c].t[e] += d[c].t[e - 1];
+                float inc = d[c].t[7];
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const float t = __shfl_up_sync(PB_FULL, inc, sft);
+                    if (lane >= sft) inc += t;
+                }
+                float ex = __shfl_up_sync(PB_FULL, inc, 1);
+                ex = (lane == 0 ? 0.f : ex) + carry;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[c].t[e] += ex;
+                carry += __shfl_sync(PB_FULL, inc, 31);
+            }
+            // the cumsum runs on into the zero fill beyond T: those inputs of the convolution must stay zero
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                if (c * 32 + lane >= n8) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d[c].t[e] = 0.f;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int v0 = 2 * (c * 32 + lane);
+            row[L::slot(v0)] = Vec16<float>{{d[c].t[0], d[c].t[1], d[c].t[2], d[c].t[3]}};
+            row[L::slot(v0 + 1)] = Vec16<float>{{d[c].t[4], d[c].t[5], d[c].t[6], d[c].t[7]}};
+        }
+        __syncwarp();
+        if (h_stride != 0 || !have_taps) {
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a) taps[a] = hs[a];
+            have_taps = true;
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            if (c * 256 < T) {                                      // warp-uniform
+                const int v0 = 2 * (c * 32 + lane);
+#pragma unroll
+                for (int w = 0; w < NPV + 2; ++w) {
+                    // causal: vectors v0 - NPV .. v0 + 1; anti-causal: v0 .. v0 + 1 + NPV
+                    const int vv = ADJ ? v0 + w : v0 - NPV + w;
+                    const Vec16<float> xv = row[L::slot(vv)];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            // sample index relative to the lane's first output: s = 4 (w - NPV) + t (causal), 4 w + t (adj)
+                            const int sidx = ADJ ? 4 * w + t : 4 * (w - NPV) + t;
+                            const int j = ADJ ? sidx - e : e - sidx;
+                            if (j >= 0 && j < KMAX) acc[e] = fmaf(taps[j >= 0 && j < KMAX ? j : 0], xv.t[t], acc[e]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[c].t[e] = acc[e];
+        }
+        if (OP == OP_HRFINTEG_ADJ) {                                // reversed cumsum (pybold/linear.py:113)
+            float carry = 0.f;
+#pragma unroll
+            for (int c = NCH - 1; c >= 0; --c) {
+#pragma unroll
+                for (int e = 6; e >= 0; --e) d[c].t[e] += d[c].t[e + 1];
+                float inc = d[c].t[0];
+#pragma unroll
+                for (int sft = 1; sft < 32; sft <<= 1) {
+                    const float t = __shfl_down_sync(PB_FULL, inc, sft);
+                    if (lane + sft < 32) inc += t;
+                }
+                float ex = __shfl_down_sync(PB_FULL, inc, 1);
+                ex = (lane == 31 ? 0.f : ex) + carry;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[c].t[e] += ex;
+                carry += __shfl_sync(PB_FULL, inc, 0);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int i = c * 32 + lane;
+            if (i < n8) stg256(out + v * T + 8 * (int64_t)i, d[c]);
+        }
+        __syncwarp();                                               // the next row overwrites the buffer
+    }
+}
+
 }  // namespace pb
