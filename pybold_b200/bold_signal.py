@@ -35,11 +35,12 @@ def _as_batch(y, dtype):
 
 
 def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e-6, wind=6,
-                 nb_iter=1000):
+                 nb_iter=1000, events=None):
     """Device entry point: tensors in, tensors out.  Returns (x, z, diff_z, J_raw, n_iter).
 
     ``J_raw[v, k]`` is the un-normalised cost of iteration k (NaN past ``n_iter[v]``);
     ``lipschitz`` is the constant actually used (0.9 x power estimate in ``deconv``).
+    ``events=(e0, e1)``: CUDA events recorded immediately around the solver launch (benchmarks).
     """
     V, T = y.shape
     dtype, dev = y.dtype, y.device
@@ -62,10 +63,14 @@ def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e
     J = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
     n_iter = torch.zeros(V, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):        # the C side sizes its grid for, and launches on, the current device
+        if events is not None:
+            events[0].record()
         rc = _lib.fn("pb_deconv", dtype)(
             ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0),
             int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
             ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
+        if events is not None:
+            events[1].record()
     _lib.check(rc, "pb_deconv")
     return x, z, dz, J, n_iter
 
