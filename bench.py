@@ -60,7 +60,7 @@ GATHER_KEYS = {"all": ("x", "z", "diff_z", "h", "theta", "J", "r", "g"), "estima
                "none": ()}
 
 
-def config_dict(w, world, scaling, gather="all"):
+def config_dict(w, world, scaling, gather="all", overlap=True):
     """Same keys and values in both arms (the driver compares them)."""
     V = w["voxels_per_gpu"]
     total = V * world if scaling == "weak" else V
@@ -72,7 +72,9 @@ def config_dict(w, world, scaling, gather="all"):
             "t_r": w["t_r"], "hrf_dur": w["hrf_dur"], "nb_iter": w["nb_iter"], "lbda": w["lbda"],
             "theta_0": w["theta_0"], "bounds": list(w["bounds"]), "scaling": scaling,
             "partition": "contiguous voxel ranges over %d rank(s)" % world,
-            "gather": ("%s (%s) over NCCL after every step" % (gather, ", ".join(GATHER_KEYS[gather]))
+            "gather": ("%s (%s) over NCCL after every step%s" % (
+                gather, ", ".join(GATHER_KEYS[gather]),
+                ", on a side stream while the next step solves" if overlap and GATHER_KEYS[gather] else "")
                        if world > 1 else "single rank, nothing to gather"),
             "l2": "GPU arm: L2 flushed between timed steps (256 MB write, excluded from the step time); "
                   "the working set of a step also exceeds the 126 MB L2"}
@@ -234,7 +236,7 @@ def run_reference(args):
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(w, args.gpus, args.scaling, args.gather),
+        "config": config_dict(w, args.gpus, args.scaling, args.gather, not args.no_overlap),
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": n_jobs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -257,6 +259,8 @@ def main():
     ap.add_argument("--nb-iter", type=int, default=WORKLOAD["nb_iter"])
     ap.add_argument("--gather", default="all", choices=["all", "estimates", "none"],
                     help="outputs gathered over NCCL after every step when N > 1")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="gather on the solver's stream instead of overlapping it with the next step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -288,7 +292,7 @@ def main():
     f32 = torch.float32
 
     w = dict(WORKLOAD, voxels_per_gpu=args.voxels, n_scans=args.scans, t_r=args.t_r, nb_iter=args.nb_iter)
-    cfg = config_dict(w, world, args.scaling, args.gather)
+    cfg = config_dict(w, world, args.scaling, args.gather, not args.no_overlap)
     T, n, K = w["n_scans"], w["nb_iter"], cfg["hrf_taps"]
     V_total = cfg["voxels_total"]
     lo, hi = voxel_range(V_total, rank, world)
@@ -318,33 +322,58 @@ def main():
 
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
-    def timed_steps(launch, gather, steps, warmup):
-        """W untimed steps, then `steps` timed ones: CUDA events on the launching stream around the
-        whole loop (minus the L2 flushes between steps), per-step events around the solver launch and
-        around the gather.  Returns (ms per step, solver kernel ms, gather ms), each the MAX over ranks."""
+    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+
+    def timed_steps(launch, gather, steps, warmup, nbuf=1):
+        """W untimed steps, then `steps` timed ones: CUDA events on the launching stream around the whole
+        loop (minus the L2 flushes between steps), per-step events around the solver launch and around the
+        gather.  ``launch(b)`` solves into output buffer b, ``gather(out, b)`` gathers it.  With two buffers
+        and N > 1 the gather of step i runs on a high-priority side stream while step i + 1 solves (the
+        solver pulls its tasks from a work queue, so the SMs NCCL occupies for a few ms cost next to
+        nothing); the last gather is exposed.  Returns (ms per step, solver ms, gather ms), MAX over ranks."""
+        main = torch.cuda.current_stream()
+        overlap = side is not None and nbuf > 1
         for _ in range(warmup):
-            gather(launch())
+            gather(launch(0), 0)
             flush.fill_(1.0)
         barrier()
-        marks = []
+        marks, gmarks = [], []
+        gather_done = [None] * nbuf
         t0, t1 = ev(), ev()
         t0.record()
-        for _ in range(steps):
-            m = [ev() for _ in range(5)]
+        for i in range(steps):
+            b = i % nbuf
+            m = [ev() for _ in range(4)]
+            if overlap and gather_done[b] is not None:
+                main.wait_event(gather_done[b])      # buffer b and its gathered copies are free again
             m[0].record()
-            out = launch()
+            out = launch(b)
             m[1].record()
-            gather(out)
+            g0, g1 = ev(), ev()
+            if overlap:
+                side.wait_event(m[1])
+                with torch.cuda.stream(side):
+                    g0.record()
+                    gather(out, b)
+                    g1.record()
+                gather_done[b] = g1
+            else:
+                g0.record()
+                gather(out, b)
+                g1.record()
             m[2].record()
             flush.fill_(1.0)           # L2 flush between timed iterations (excluded from the step time)
             m[3].record()
             marks.append(m)
+            gmarks.append((g0, g1))
+        if overlap:
+            main.wait_stream(side)
         t1.record()
         barrier()
         total = t0.elapsed_time(t1)
         flush_ms = sum(m[2].elapsed_time(m[3]) for m in marks)
         kern = [m[0].elapsed_time(m[1]) for m in marks]
-        gath = [m[1].elapsed_time(m[2]) for m in marks]
+        gath = [a.elapsed_time(b_) for a, b_ in gmarks]
         step_ms, kern_ms, gath_ms = max_over_ranks([(total - flush_ms) / steps, sum(kern) / steps,
                                                     sum(gath) / steps])
         return step_ms, kern_ms, gath_ms, kern
@@ -352,20 +381,21 @@ def main():
     # ---- headline: device-resident inputs, reusable outputs: a step = one kernel launch (+ gather) ----
     lbda_dev = torch.full((1,), w["lbda"], dtype=f32, device=dev)
     theta0_dev = torch.full((1,), w["theta_0"], dtype=f32, device=dev)
-    out_buf = bd_alloc(V, T, K, n, f32, dev)
-    gathered = {}
+    nbuf = 2 if (world > 1 and keys and not args.no_overlap) else 1
+    out_buf = [bd_alloc(V, T, K, n, f32, dev) for _ in range(nbuf)]
+    gathered = [{} for _ in range(nbuf)]
 
-    def launch():
+    def launch(b):
         return bd_batch(y_dev, w["t_r"], lbda_dev, theta0_dev, None, w["hrf_dur"], [w["bounds"]],
-                        n, False, 4, 1.0e-12, out=out_buf)
+                        n, False, 4, 1.0e-12, out=out_buf[b])
 
-    def gather(out):
+    def gather(out, b):
         if world > 1 and keys:   # final gather of the outputs; never inside the solve
-            gather_outputs(out, V_total, keys, into=gathered)
+            gather_outputs(out, V_total, keys, into=gathered[b])
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        gather(launch())
+    for i in range(warm):
+        gather(launch(i % nbuf), i % nbuf)
     barrier()
 
     # ---- FP32 FMA microbenchmark (second roofline denominator), same run, same clocks regime ----
@@ -386,7 +416,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    step_ms, kern_ms, gath_ms, solver_ms = timed_steps(launch, gather, args.steps, 0)
+    step_ms, kern_ms, gath_ms, solver_ms = timed_steps(launch, gather, args.steps, 0, nbuf)
     clocks = sampler.stop() if rank == 0 else None
     value = V_total / (step_ms * 1e-3)
 
@@ -449,8 +479,7 @@ def main():
     extra = {}
     launches = args.steps
     if not args.no_extra:
-        del out_buf, y_dev
-        gathered.clear()
+        del out_buf, y_dev, gathered
         torch.cuda.empty_cache()
         x_steps, x_warm = 2, 1
 
@@ -460,18 +489,19 @@ def main():
         lo4, hi4 = voxel_range(c4["voxels_total"], rank, world)
         V4, T4, n4 = hi4 - lo4, c4["n_scans"], c4["nb_iter"]
         y4 = gen_voxels_device(V4, T4, c4["t_r"], c4["hrf_dur"], seed=4, first_voxel=lo4, dtype=f32)
-        o4 = bd_alloc(V4, T4, K4, n4, f32, dev)
-        g4 = {}
+        nb4 = 2 if (world > 1 and not args.no_overlap) else 1
+        o4 = [bd_alloc(V4, T4, K4, n4, f32, dev) for _ in range(nb4)]
+        g4 = [{} for _ in range(nb4)]
 
-        def launch4():
+        def launch4(b):
             return bd_batch(y4, c4["t_r"], lbda_dev, theta0_dev, None, c4["hrf_dur"], [c4["bounds"]],
-                            n4, False, 4, 1.0e-12, out=o4)
+                            n4, False, 4, 1.0e-12, out=o4[b])
 
-        def gather4(out):
+        def gather4(out, b):
             if world > 1:
-                gather_outputs(out, c4["voxels_total"], ALL_OUTPUTS, into=g4)
+                gather_outputs(out, c4["voxels_total"], ALL_OUTPUTS, into=g4[b])
 
-        s_ms, k_ms, g_ms, _ = timed_steps(launch4, gather4, x_steps, x_warm)
+        s_ms, k_ms, g_ms, _ = timed_steps(launch4, gather4, x_steps, x_warm, nb4)
         launches += x_steps
         (v4max,) = max_over_ranks([float(V4)])
         extra["cfg4_bd_230k_x_1200"] = {
@@ -482,8 +512,7 @@ def main():
             "hrf_taps": K4, "nb_iter": n4, "data": "synthetic (device generator philox-v1, seed 4)",
             "roofline": fp32_roofline("bd", int(v4max), T4, K4, n4, k_ms,
                                       "variant %d" % _lib.lib.pb_solver_variant(T4, K4, 0))}
-        del y4, o4
-        g4.clear()
+        del y4, o4, g4
         torch.cuda.empty_cache()
 
         if world == 1:
@@ -493,8 +522,8 @@ def main():
             o64 = bd_alloc(V, T, K, n, f64, dev)
             lb64, th64 = lbda_dev.to(f64), theta0_dev.to(f64)
             s_ms, k_ms, _, _ = timed_steps(
-                lambda: bd_batch(y64, w["t_r"], lb64, th64, None, w["hrf_dur"], [w["bounds"]], n, False, 4,
-                                 1.0e-12, out=o64), lambda out: None, x_steps, x_warm)
+                lambda b: bd_batch(y64, w["t_r"], lb64, th64, None, w["hrf_dur"], [w["bounds"]], n, False, 4,
+                                   1.0e-12, out=o64), lambda out, b: None, x_steps, x_warm)
             launches += x_steps
             fl = flops_bd_voxel(T, K, n) * V / (k_ms * 1e-3) / 1e12
             extra["cfg3_bd_fp64_build"] = {
@@ -518,11 +547,11 @@ def main():
             lb2 = torch.full((1,), c2["lbda"], dtype=f32, device=dev)
             k_evs = []
 
-            def launch2():
+            def launch2(b):
                 k_evs.append((ev(), ev()))
                 return deconv_batch(y2, h2, lb2, L2t, None, False, 1.0e-6, 6, c2["nb_iter"], events=k_evs[-1])
 
-            s_ms, _, _, _ = timed_steps(launch2, lambda out: None, 5, 3)
+            s_ms, _, _, _ = timed_steps(launch2, lambda out, b: None, 5, 3)
             # the launch is so short that events around the Python call would time the host: these two sit
             # immediately around the C-ABI launch (the momentum-table kernel is part of the launch)
             k_ms = sum(a.elapsed_time(b) for a, b in k_evs[-5:]) / 5
@@ -549,10 +578,10 @@ def main():
             from pybold_b200.bold_signal import deconv_lbda_path
             problems = c5["n_lbda"] * c5["voxels"]
 
-            def path():
+            def path(b):
                 return deconv_lbda_path(y5, c5["t_r"], h5, lbdas, nb_iter=c5["nb_iter"], x0=x05)
 
-            s_ms, k_ms, _, _ = timed_steps(path, lambda out: None, 2, 1)
+            s_ms, k_ms, _, _ = timed_steps(path, lambda out, b: None, 2, 1)
             launches += 2
             extra["cfg5_lbda_path_64_x_20k_x_600"] = {
                 "workload": "deconv_path_%d_lbda_x_%dk_voxels_x_%d_TRs" % (c5["n_lbda"], c5["voxels"] // 1000,

@@ -409,7 +409,8 @@ template <int R, int KMAX, int NW>
 bool fastc_shape_ok(int T, int K) {
     // the last used thread may be partial, threads beyond it idle; up to half of the threads may idle
     // (the dispatcher picks the variant with the fewest slots among those that match)
-    return K <= KMAX && T <= NW * 32 * R && T > NW * 16 * R - R && T >= 1;
+    // (the smallest variant, one warp of R = 4, also takes everything shorter)
+    return K <= KMAX && T <= NW * 32 * R && (T > NW * 16 * R - R || (NW == 1 && R == 4)) && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int NW, int MINB>

@@ -305,6 +305,30 @@ def test_bd_long_series_four_warp_variant_vs_generic_fp64():
         assert rel(d32["J"], d["J"]) < 1e-4 and np.max(np.abs(d32["theta"] - d["theta"])) < 1e-4
 
 
+@pytest.mark.parametrize("T,t_r,n_it", [(200, 0.5, 12), (600, 0.5, 8), (90, 0.5, 10), (40, 0.5, 10), (1000, 0.5, 6),
+                                        (2000, 0.5, 4), (3000, 0.5, 3), (300, 0.32, 10), (1200, 0.32, 5),
+                                        (4096, 0.32, 3), (3000, 1.0, 3), (4096, 0.72, 3), (2600, 1.0, 4)])
+def test_bd_short_tr_and_long_series_variants(T, t_r, n_it):
+    """Round 2 variants: 28 < K <= 64 taps (TR 0.5 s -> K = 40, TR 0.32 s -> K = 63) and 2560 < T <= 4096
+    (eight warps per voxel) run register-tiled in FP32; the FP64 build of these shapes is the generic
+    shared-memory kernel: two independent implementations, north_star's 1e-4."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    K = pb.hrf_model.hrf_len(t_r, 20.0)
+    assert _lib.lib.pb_solver_variant(T, K, 0) != 0
+    y = gen_voxels(3, T, t_r, 20.0, seed0=7500 + T)
+    x, z, dz, h, d = pb.bd(y, t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0, nb_iter=n_it)
+    x32, z32, dz32, h32, d32 = pb.bd(y.astype(np.float32), t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0,
+                                     nb_iter=n_it)
+    assert h32.shape == (3, K)
+    assert rel(z32, z) < 1e-4 and rel(x32, x) < 1e-4 and rel(h32, h) < 1e-4
+    assert rel(d32["J"], d["J"]) < 1e-4 and np.max(np.abs(d32["theta"] - d["theta"])) < 1e-4
+    if T <= 300:
+        xo, zo, wo, ho, do = orc.bd(y[1], t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0, nb_iter=n_it,
+                                    theta_solver="exact")
+        assert rel(z32[1], zo) < 1e-4 and rel(h32[1], ho) < 1e-4 and rel(d32["J"][1], do["J"]) < 1e-4
+
+
 def test_bd_streamed_host_batch_equals_single_launch():
     """Host batches above the streaming threshold are solved chunk by chunk with overlapped copies;
     the result must be bit-identical to the single-launch path, including per-voxel parameters

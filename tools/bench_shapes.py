@@ -1,22 +1,46 @@
-"""Developer measurement: bd throughput at series lengths between the tuned shapes (which register-tiled
-variant the dispatcher picks and what it delivers)."""
-import sys, torch, json
+"""Developer measurement: bd throughput over series lengths and tap counts (which register-tiled variant
+the dispatcher picks and what fraction of the nominal FP32 peak it delivers).
+
+    python tools/bench_shapes.py [nb_iter] > profiles/rNN_shapes.txt
+
+Every shape runs two full waves of its persistent grid (no tail effect); flops as in bench.py.
+"""
+import sys
+import torch
 sys.path.insert(0, ".")
+from bench import flops_bd_voxel
 from pybold_b200 import _lib
 from pybold_b200.bold_signal import bd_alloc, bd_batch
 from pybold_b200.hrf_model import hrf_len
 from pybold_b200.synth import gen_voxels_device
-for T, t_r, V in [(100, 1.0, 80000), (128, 0.72, 60000), (150, 1.0, 60000), (190, 1.0, 50000), (350, 1.0, 40000), (330, 0.72, 40000), (405, 1.0, 30000), (500, 0.72, 24000), (650, 1.0, 20000),
-                  (700, 0.72, 16000), (800, 0.72, 16000), (900, 0.72, 14000), (1000, 0.72, 12000), (1050, 0.72, 12000), (1150, 0.72, 12000), (2000, 0.72, 6000), (2400, 1.0, 6000)]:
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+sms = torch.cuda.get_device_properties(0).multi_processor_count
+nominal = sms * 128 * 2 * 1.965e9 / 1e12
+Ts = [64, 96, 100, 128, 150, 190, 200, 240, 256, 300, 320, 350, 384, 405, 450, 500, 512, 600, 650, 700, 768, 800,
+      900, 1000, 1050, 1150, 1200, 1280, 1500, 2000, 2400, 2560, 3000, 4096]
+print("bd, FP32, nb_iter = %d, two waves of the grid per shape; fraction of the nominal FP32 peak (%.1f Tflop/s)" % (n, nominal))
+print("%5s %3s %10s %8s %9s %11s %8s %6s" % ("T", "K", "variant", "voxels", "ms", "voxels/s", "Tflop/s", "frac"))
+worst = {}
+for t_r in (1.0, 0.75, 0.72, 0.5, 0.32):
     K = hrf_len(t_r, 20.0)
-    y = gen_voxels_device(V, T, t_r, 20.0)
-    out = bd_alloc(V, T, K, 100, torch.float32, y.device)
-    lb = torch.full((1,), 1.7, device="cuda"); th = torch.full((1,), 2.0, device="cuda")
-    f = lambda: bd_batch(y, t_r, lb, th, None, 20.0, [(0.6, 1.9)], 100, False, 4, 1e-12, out=out)
-    f(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); f(); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    mac = T * K - K * (K - 1) // 2
-    fl = V * (101 * 100 * (4 * mac + 11 * T))
-    print(T, K, "variant", _lib.lib.pb_solver_variant(T, K, 0), "%.1f ms %.0f vox/s %.1f Tflop/s" % (ms, V / ms * 1e3, fl / ms / 1e9), flush=True)
+    for T in Ts:
+        wave = _lib.lib.pb_bd_wave_voxels(T, K, 0, n)
+        V = 2 * wave if wave > 0 else 2000
+        y = gen_voxels_device(V, T, t_r, 20.0)
+        out = bd_alloc(V, T, K, n, torch.float32, y.device)
+        lb = torch.full((1,), 1.7, device="cuda"); th = torch.full((1,), 2.0, device="cuda")
+        f = lambda: bd_batch(y, t_r, lb, th, None, 20.0, [(0.6, 1.9)], n, False, 4, 1e-12, out=out)
+        f(); torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); f(); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tf = flops_bd_voxel(T, K, n) * V / best / 1e9
+        vid = _lib.lib.pb_solver_variant(T, K, 0)
+        print("%5d %3d %10d %8d %9.2f %11.0f %8.1f %6.2f" % (T, K, vid, V, best, V / best * 1e3, tf, tf / nominal), flush=True)
+        if T <= 2560:
+            worst[K] = min(worst.get(K, 9), tf / nominal)
+        del y, out
+print("lowest fraction for 64 <= T <= 2560 per tap count:", {k: round(v, 2) for k, v in worst.items()})
