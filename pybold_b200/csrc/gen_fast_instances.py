@@ -68,6 +68,11 @@ CVARIANTS = [
     # round 2: eight warps per voxel for 2540 < T <= 5120 (PB_MAX_T = 4096)
     ("float", 20, 20, 8, 2),
     ("float", 20, 28, 8, 2),
+    # round 2: K <= 20 at 640 < T <= 1280 ran the 28-tap tile; three warps per voxel for 1260 < T <= 1920
+    # (T = 1500 filled 59 % of the four-warp variant's slots)
+    ("float", 20, 20, 2, 6),
+    ("float", 20, 20, 3, 4),
+    ("float", 20, 28, 3, 4),
 ] + [
     # round 2: short-TR acquisitions, 28 < K <= 40 (TR >= 0.5 s) and K <= 64 (TR >= 0.32 s), every T <= 4096.
     # More taps, more registers (taps, halo and tile live in registers): launch bounds leave ~170 (K = 40)

@@ -409,8 +409,9 @@ template <int R, int KMAX, int NW>
 bool fastc_shape_ok(int T, int K) {
     // the last used thread may be partial, threads beyond it idle; up to half of the threads may idle
     // (the dispatcher picks the variant with the fewest slots among those that match)
-    // (the smallest variant, one warp of R = 4, also takes everything shorter)
-    return K <= KMAX && T <= NW * 32 * R && (T > NW * 16 * R - R || (NW == 1 && R == 4)) && T >= 1;
+    // (the smallest variants of the many-tap families, one warp of R = 4, also take everything shorter;
+    // with K <= 32 short series are better served by the group / warp kernels)
+    return K <= KMAX && T <= NW * 32 * R && (T > NW * 16 * R - R || (NW == 1 && R == 4 && K > 32)) && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int NW, int MINB>

@@ -11,6 +11,19 @@
 #pragma once
 #include "pb_device.cuh"
 
+// The outer phases are real function calls (not inlined into the solver kernels): ptxas then allocates the
+// registers of the inner loop without the FP64 temporaries of these phases in the picture (inlined, every edit
+// here re-shuffled the inner loop's allocation and its operand-reuse pattern, profiles/r01_rf_bandwidth.txt),
+// and the state that lives across a call is saved once per outer iteration, i.e. once per nb_iter inner ones.
+#ifdef PB_OUTER_NOINLINE
+#define PB_OUTER_FN __device__ __noinline__
+#else
+#define PB_OUTER_FN __device__ __forceinline__
+#endif
+#ifndef PB_EVAL_SPLIT
+#define PB_EVAL_SPLIT 0     /* 1: two accumulators per dot product in theta_eval_group (spills into the inner loop) */
+#endif
+
 namespace pb {
 
 template <int G>
@@ -21,8 +34,8 @@ __device__ __forceinline__ double group_sum_f64(double v) {
 }
 
 template <int G>
-__device__ __forceinline__ void hrf_eval_group(double theta, const HrfGrid &grid, ThetaScratch &sc,
-                                               int q) {
+__device__ __forceinline__ void hrf_eval_group_inl(double theta, const HrfGrid &grid, ThetaScratch &sc,
+                                                   int q) {
     for (int a = q; a < grid.K; a += G) {
         double h, h1, h2;
         hrf_tap(theta, grid.t(a), h, h1, h2);
@@ -33,60 +46,121 @@ __device__ __forceinline__ void hrf_eval_group(double theta, const HrfGrid &grid
     __syncwarp();
 }
 
-// same formula as frob_lipschitz_warp (pb_device.cuh), lanes of the group stride over the lags
 template <int G>
-__device__ __forceinline__ double frob_lipschitz_group(ThetaScratch &sc, int K, int T, int q) {
-    if (q == 0) {
-        double c = 0.0, S = 0.0;
-        for (int m = 0; m < K; ++m) {
-            c += sc.hs[m];
-            sc.cs[m] = c;
-            S += c;
-            sc.Ss[m] = S;
+PB_OUTER_FN void hrf_eval_group(double theta, HrfGrid grid, ThetaScratch sc, int q) {
+    hrf_eval_group_inl<G>(theta, grid, sc, q);
+}
+
+// same formula as frob_lipschitz_warp (pb_device.cuh), lanes of the group stride over the lags.
+// These phases are latency bound (dependent FP64 chains, one warp instruction every ~14 cycles in the
+// round-1 profile, 20 % of the warp time of the cfg3 kernel for 5.5 % of its instructions), so the loops
+// below keep several independent chains in flight: a lane works on its two lags (d = q and d = q + G)
+// in the same loop instead of one after the other, and plain sums are split over four accumulators.
+template <int G>
+PB_OUTER_FN double frob_lipschitz_group(ThetaScratch sc, int K, int T, int q) {
+    // cs = cumsum(h), Ss = cumsum(cs): Ss[m] = sum_j (m - j + 1) h[j]; every lane sums its own entries
+    for (int m = q; m < K; m += G) {
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = 0;
+        for (; j + 3 <= m; j += 4) {
+            const double h0 = sc.hs[j], h1 = sc.hs[j + 1], h2 = sc.hs[j + 2], h3 = sc.hs[j + 3];
+            c0 += h0;
+            c1 += h1;
+            c2 += h2;
+            c3 += h3;
+            s0 = fma((double)(m - j + 1), h0, s0);
+            s1 = fma((double)(m - j), h1, s1);
+            s2 = fma((double)(m - j - 1), h2, s2);
+            s3 = fma((double)(m - j - 2), h3, s3);
         }
+        for (; j <= m; ++j) {
+            const double h0 = sc.hs[j];
+            c0 += h0;
+            s0 = fma((double)(m - j + 1), h0, s0);
+        }
+        sc.cs[m] = (c0 + c1) + (c2 + c3);
+        sc.Ss[m] = (s0 + s1) + (s2 + s3);
     }
     __syncwarp();
     const int E = K - 1;
     const double C = sc.cs[K - 1];
     double total = 0.0;
-    for (int d = q; d < E && d < T; d += G) {
-        double acc = 0.0, ss = 0.0;
-        const int nmax = min(E - 1, T - 1 - d);
-        for (int m = 0; m <= nmax; ++m) {
-            const int md = m + d;
-            acc = fma(sc.cs[m], sc.cs[md < K - 1 ? md : K - 1], acc);
-            ss = fma(acc, acc, ss);
+    for (int d0 = q; d0 < E && d0 < T; d0 += 2 * G) {
+        // two lags per pass: d0 and d1 = d0 + G (independent chains)
+        const int d1 = d0 + G;
+        const bool on1 = d1 < E && d1 < T;
+        double acc0 = 0.0, ss0 = 0.0, acc1 = 0.0, ss1 = 0.0;
+        const int n0 = min(E - 1, T - 1 - d0), n1 = on1 ? min(E - 1, T - 1 - d1) : -1;
+        const int nn = n0 > n1 ? n0 : n1;
+        for (int m = 0; m <= nn; ++m) {
+            const double cm = sc.cs[m];
+            const int m0 = m + d0, m1 = m + d1;
+            if (m <= n0) {
+                acc0 = fma(cm, sc.cs[m0 < K - 1 ? m0 : K - 1], acc0);
+                ss0 = fma(acc0, acc0, ss0);
+            }
+            if (m <= n1) {
+                acc1 = fma(cm, sc.cs[m1 < K - 1 ? m1 : K - 1], acc1);
+                ss1 = fma(acc1, acc1, ss1);
+            }
         }
-        const int Q = T - d - E;
-        if (Q > 0) {
-            const double a = acc, e = C * C, qq = (double)Q;
-            ss += qq * a * a + a * e * qq * (qq + 1.0) + e * e * qq * (qq + 1.0) * (2.0 * qq + 1.0) / 6.0;
+        const double e = C * C;
+        const int Q0 = T - d0 - E, Q1 = T - d1 - E;
+        if (Q0 > 0) {
+            const double a = acc0, qq = (double)Q0;
+            ss0 += qq * a * a + a * e * qq * (qq + 1.0) + e * e * qq * (qq + 1.0) * (2.0 * qq + 1.0) / 6.0;
         }
-        total += (d == 0 ? 1.0 : 2.0) * ss;
+        if (on1 && Q1 > 0) {
+            const double a = acc1, qq = (double)Q1;
+            ss1 += qq * a * a + a * e * qq * (qq + 1.0) + e * e * qq * (qq + 1.0) * (2.0 * qq + 1.0) / 6.0;
+        }
+        total += (d0 == 0 ? 1.0 : 2.0) * ss0;
+        if (on1) total += 2.0 * ss1;
     }
     const double SE = E > 0 ? sc.Ss[E - 1] : 0.0;
     const double dup = (E == 0) ? 1.0 : 0.0;
-    for (int n = q; n < T - E; n += G) {
-        const double St = n < E ? sc.Ss[n] : SE + C * (double)(n - E + 1);
-        const double wgt = 2.0 * (double)(T - n - E) - dup;
-        const double v = C * St;
-        total = fma(wgt * v, v, total);
+    double tt[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int n = q; n < T - E; n += 4 * G) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int nu = n + u * G;
+            if (nu < T - E) {
+                const double St = nu < E ? sc.Ss[nu] : SE + C * (double)(nu - E + 1);
+                const double wgt = 2.0 * (double)(T - nu - E) - dup;
+                const double v = C * St;
+                tt[u] = fma(wgt * v, v, tt[u]);
+            }
+        }
     }
-    total = group_sum_f64<G>(total);
+    const double t0 = tt[0] + tt[2], t1 = tt[1] + tt[3];
+    total = group_sum_f64<G>(total + (t0 + t1));
     __syncwarp();
     return sqrt(total);
 }
 
 template <int G>
-__device__ __forceinline__ void gram_build_group(ThetaScratch &sc, int K, int q) {
-    for (int d = q; d < K; d += G) {
-        double acc = sc.Rz[d];
-        sc.M[d] = acc;
-        sc.M[d * sc.KS] = acc;
-        for (int n = 1; n + d < K; ++n) {
-            acc = fma(-sc.zend[n - 1], sc.zend[n - 1 + d], acc);
-            sc.M[n * sc.KS + n + d] = acc;
-            sc.M[(n + d) * sc.KS + n] = acc;
+PB_OUTER_FN void gram_build_group(ThetaScratch sc, int K, int q) {
+    // diagonals d0 = q and d1 = q + G in the same loop (two independent recurrences)
+    for (int d0 = q; d0 < K; d0 += 2 * G) {
+        const int d1 = d0 + G;
+        const bool on1 = d1 < K;
+        double acc0 = sc.Rz[d0], acc1 = on1 ? sc.Rz[d1] : 0.0;
+        sc.M[d0] = acc0;
+        sc.M[d0 * sc.KS] = acc0;
+        if (on1) {
+            sc.M[d1] = acc1;
+            sc.M[d1 * sc.KS] = acc1;
+        }
+        for (int n = 1; n + d0 < K; ++n) {
+            const double ze = sc.zend[n - 1];
+            acc0 = fma(-ze, sc.zend[n - 1 + d0], acc0);
+            sc.M[n * sc.KS + n + d0] = acc0;
+            sc.M[(n + d0) * sc.KS + n] = acc0;
+            if (n + d1 < K) {
+                acc1 = fma(-ze, sc.zend[n - 1 + d1], acc1);
+                sc.M[n * sc.KS + n + d1] = acc1;
+                sc.M[(n + d1) * sc.KS + n] = acc1;
+            }
         }
     }
     __syncwarp();
@@ -95,20 +169,50 @@ __device__ __forceinline__ void gram_build_group(ThetaScratch &sc, int K, int q)
 template <int G>
 __device__ __forceinline__ void theta_eval_group(double theta, const HrfGrid &grid, ThetaScratch &sc,
                                                  int q, double &g, double &c) {
-    hrf_eval_group<G>(theta, grid, sc, q);
+    hrf_eval_group_inl<G>(theta, grid, sc, q);
     const int K = grid.K;
     double pg = 0.0, pc = 0.0;
-    for (int a = q; a < K; a += G) {
-        double qa = -sc.b[a], q1 = 0.0;
-        const double *row = sc.M + a * sc.KS;
-        for (int bb = 0; bb < K; ++bb) {
-            const double m = row[bb];
-            qa = fma(m, sc.hs[bb], qa);
-            q1 = fma(m, sc.h1s[bb], q1);
+    // rows a0 = q and a1 = q + G of M in the same loop, each dot product over two accumulators: eight
+    // independent DFMA chains instead of two (these quadratic forms were 24 % of the outer-phase time)
+    for (int a0 = q; a0 < K; a0 += 2 * G) {
+        const int a1 = a0 + G;
+        const bool on1 = a1 < K;
+        const double *r0 = sc.M + a0 * sc.KS;
+        const double *r1 = sc.M + (on1 ? a1 : a0) * sc.KS;
+        double qa0 = -sc.b[a0], qa0b = 0.0, q10 = 0.0, q10b = 0.0;
+        double qa1 = on1 ? -sc.b[a1] : 0.0, qa1b = 0.0, q11 = 0.0, q11b = 0.0;
+        int bb = 0;
+        for (; PB_EVAL_SPLIT && bb + 1 < K; bb += 2) {
+            const double ha = sc.hs[bb], hb = sc.hs[bb + 1], da = sc.h1s[bb], db = sc.h1s[bb + 1];
+            const double m0a = r0[bb], m0b = r0[bb + 1], m1a = r1[bb], m1b = r1[bb + 1];
+            qa0 = fma(m0a, ha, qa0);
+            qa0b = fma(m0b, hb, qa0b);
+            q10 = fma(m0a, da, q10);
+            q10b = fma(m0b, db, q10b);
+            qa1 = fma(m1a, ha, qa1);
+            qa1b = fma(m1b, hb, qa1b);
+            q11 = fma(m1a, da, q11);
+            q11b = fma(m1b, db, q11b);
         }
-        pg = fma(sc.h1s[a], qa, pg);
-        pc = fma(sc.h1s[a], q1, pc);
-        pc = fma(sc.h2s[a], qa, pc);
+        for (; bb < K; ++bb) {
+            const double ha = sc.hs[bb], da = sc.h1s[bb];
+            qa0 = fma(r0[bb], ha, qa0);
+            q10 = fma(r0[bb], da, q10);
+            qa1 = fma(r1[bb], ha, qa1);
+            q11 = fma(r1[bb], da, q11);
+        }
+        {
+            const double qa = qa0 + qa0b, q1 = q10 + q10b;
+            pg = fma(sc.h1s[a0], qa, pg);
+            pc = fma(sc.h1s[a0], q1, pc);
+            pc = fma(sc.h2s[a0], qa, pc);
+        }
+        if (on1) {
+            const double qa = qa1 + qa1b, q1 = q11 + q11b;
+            pg = fma(sc.h1s[a1], qa, pg);
+            pc = fma(sc.h1s[a1], q1, pc);
+            pc = fma(sc.h2s[a1], qa, pc);
+        }
     }
     g = group_sum_f64<G>(pg);
     c = group_sum_f64<G>(pc);
@@ -116,9 +220,8 @@ __device__ __forceinline__ void theta_eval_group(double theta, const HrfGrid &gr
 }
 
 template <int G>
-__device__ __forceinline__ double theta_solve_group(double theta_prev, double lo, double hi,
-                                                    const HrfGrid &grid, ThetaScratch &sc, int q,
-                                                    int *n_eval) {
+PB_OUTER_FN double theta_solve_group(double theta_prev, double lo, double hi, HrfGrid grid, ThetaScratch sc,
+                                     int q, int *n_eval) {
     enum { INIT = 0, BRACKET = 1, NEWTON = 2, DONE = 3 };
     const int max_iter = 100;
     int phase = INIT, it = 0, evals = 0;
