@@ -74,6 +74,10 @@ CVARIANTS = [
     ("float", 20, 20, 3, 4),
     ("float", 20, 28, 3, 4),
 ] + [
+    # round 2: R = 16 with the skewed shared-memory layout (pb_fastc.cuh: SKEW): fills the gaps between the
+    # R = 12 and R = 20 variants -- T in (384, 512], (768, 1024], (1152, 1536], (1536, 2048], (3072, 4096]
+    ("float", 16, K, NW, M) for K in (20, 28) for (NW, M) in ((1, 12), (2, 6), (3, 4), (4, 3), (8, 2))
+] + [
     # round 2: short-TR acquisitions, 28 < K <= 40 (TR >= 0.5 s) and K <= 64 (TR >= 0.32 s), every T <= 4096.
     # More taps, more registers (taps, halo and tile live in registers): launch bounds leave ~170 (K = 40)
     # and ~250 (K = 64) registers per thread

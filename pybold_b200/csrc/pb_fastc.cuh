@@ -58,7 +58,16 @@ struct CtaLayout {
     static constexpr int NT = NW * 32;
     static constexpr int SLOTS = NT * R;
     static constexpr int PAD = (KMAX + 3) & ~3;               // >= KMAX - 1, keeps float4 alignment
-    static constexpr int BUF = PAD + SLOTS + PAD;
+    // R = 8 / 16: the per-thread stride of R floats is a multiple of 8 banks and the 16-byte stores / loads
+    // of a quarter warp would collide (round 1 measured R = 16 at 29 instead of 42 Tflop/s per slot and did
+    // not build it).  SKEW inserts 4 unused floats after every 32 samples: sample i lives at
+    // i + 4 (i >> 5), a thread's block and every aligned vector stay contiguous, and consecutive threads'
+    // vectors fall into distinct banks again.  (i >> 5 is an arithmetic shift: the zero pad before the
+    // series, i in [-PAD, -1], lands at i - 4.)
+    static constexpr bool SKEW = R % 8 == 0;
+    static constexpr int PADB = SKEW ? PAD + 8 : PAD;         // zero pad before sample 0
+    __host__ __device__ static constexpr int pos(int i) { return SKEW ? i + ((i >> 5) << 2) : i; }
+    static constexpr int BUF = PADB + pos(SLOTS + PAD) + 4;
     static constexpr int RED = NW * (2 * KMAX + 4);           // doubles for CTA-wide reductions
     __host__ __device__ static constexpr size_t bytes(int nb_iter) {
         return (((size_t)nb_iter * sizeof(real) + 15) & ~(size_t)15) +
@@ -88,13 +97,9 @@ fast_bdc_kernel(BdArgs<real> p) {
     double *bcast = totr + NW;                                // [4]  theta, Lipschitz, ...
     real *bufA = reinterpret_cast<real *>(bcast + 4);         // w / z with zero pads
     real *bufB = bufA + L::BUF;                               // residual with zero pads
-    for (int i = tid; i < L::PAD; i += L::NT) {
-        bufA[i] = real(0);
-        bufA[L::PAD + L::SLOTS + i] = real(0);
-        bufB[i] = real(0);
-        bufB[L::PAD + L::SLOTS + i] = real(0);
-    }
-    real *myA = bufA + L::PAD + tid * R, *myB = bufB + L::PAD + tid * R;
+    for (int i = tid; i < 2 * L::BUF; i += L::NT) bufA[i] = real(0);   // zero pads (and everything else once)
+    real *const baseA = bufA + L::PADB, *const baseB = bufB + L::PADB;  // sample 0 of the two buffers
+    real *myA = baseA + L::pos(tid * R), *myB = baseB + L::pos(tid * R);
     const int T = p.T, K = p.K, ntr = p.nb_iter + 2;
     const int i0 = tid * R;
     const int nvalid = max(0, min(R, T - i0));
@@ -117,7 +122,8 @@ fast_bdc_kernel(BdArgs<real> p) {
     auto halo_before = [&](const real *mine, real (&hal)[4 * NH]) {
 #pragma unroll
         for (int c = 0; c < NH; ++c) {
-            const V4 t = reinterpret_cast<const V4 *>(mine)[-1 - c];
+            const V4 t = L::SKEW ? *reinterpret_cast<const V4 *>(mine - L::pos(i0) + L::pos(i0 - 4 * (c + 1)))
+                                 : reinterpret_cast<const V4 *>(mine)[-1 - c];
 #pragma unroll
             for (int e = 0; e < 4; ++e) hal[4 * c + (3 - e)] = t.t[e];
         }
@@ -126,7 +132,8 @@ fast_bdc_kernel(BdArgs<real> p) {
     auto halo_after = [&](const real *mine, real (&hal)[4 * NH]) {
 #pragma unroll
         for (int c = 0; c < NH; ++c) {
-            const V4 t = reinterpret_cast<const V4 *>(mine + R)[c];
+            const V4 t = L::SKEW ? *reinterpret_cast<const V4 *>(mine - L::pos(i0) + L::pos(i0 + R + 4 * c))
+                                 : reinterpret_cast<const V4 *>(mine + R)[c];
 #pragma unroll
             for (int e = 0; e < 4; ++e) hal[4 * c + e] = t.t[e];
         }
@@ -411,7 +418,10 @@ bool fastc_shape_ok(int T, int K) {
     // (the dispatcher picks the variant with the fewest slots among those that match)
     // (the smallest variants of the many-tap families, one warp of R = 4, also take everything shorter;
     // with K <= 32 short series are better served by the group / warp kernels)
-    return K <= KMAX && T <= NW * 32 * R && (T > NW * 16 * R - R || (NW == 1 && R == 4 && K > 32)) && T >= 1;
+    // the many-tap families (KMAX >= 40) only serve K > 28: with fewer taps the K <= 28 variants, the group
+    // and the warp kernels are the better choice
+    return K <= KMAX && (KMAX <= 32 || K > 28) && T <= NW * 32 * R &&
+           (T > NW * 16 * R - R || (NW == 1 && R == 4)) && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int NW, int MINB>

@@ -112,8 +112,8 @@ def test_dispatch_covers_every_series_length():
     assert _lib.lib.pb_solver_variant(1200, 28, 0) == 64020028       # cfg4: two warps per voxel
     assert _lib.lib.pb_solver_variant(600, 20, 0) == 32020020
     assert _lib.lib.pb_solver_variant(150, 20, 0) // 1000000 == 8    # four voxels per warp
-    assert _lib.lib.pb_solver_variant(2000, 28, 0) // 1000000 == 128
-    assert _lib.lib.pb_solver_variant(3000, 20, 0) == 256020020      # eight warps per voxel
+    assert _lib.lib.pb_solver_variant(2000, 28, 0) == 128016028     # four warps, R = 16 (skewed layout)
+    assert _lib.lib.pb_solver_variant(3000, 20, 0) == 256016020      # eight warps per voxel
     # round 2: every K <= 64 (TR down to 0.32 s at hrf_dur = 20 s) and T <= 4096 has a register-tiled variant
     for K in (29, 40, 41, 64):
         for T in list(range(1, 200, 3)) + list(range(200, 4097, 37)) + [4096]:

@@ -296,7 +296,7 @@ def test_bd_long_series_four_warp_variant_vs_generic_fp64():
     from pybold_b200 import _lib
     for T, t_r in ((2000, 0.72), (1300, 1.0), (2560, 1.0)):
         K = pb.hrf_model.hrf_len(t_r, 20.0)
-        assert _lib.lib.pb_solver_variant(T, K, 0) // 1000000 == 128 and _lib.lib.pb_solver_variant(T, K, 1) == 0
+        assert _lib.lib.pb_solver_variant(T, K, 0) // 1000000 in (96, 128) and _lib.lib.pb_solver_variant(T, K, 1) == 0
         y = gen_voxels(3, T, t_r, 20.0, seed0=7000 + T)
         x, z, dz, h, d = pb.bd(y, t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0, nb_iter=8)
         x32, z32, dz32, h32, d32 = pb.bd(y.astype(np.float32), t_r, lbda=1.4, theta_0=2.0, hrf_dur=20.0,

@@ -128,6 +128,31 @@ int main(int argc, char **argv) {
         rung<20, 20, 16, 8, 4, 3, 0, 2>("G16 R20 SMH2 M3", b, 100);
         rung<20, 20, 16, 8, 4, 4, 1, 2>("G16 R20 SMH2 LEAN1 M4", b, 100);
         b.free_all();
+    } else if (set == 6) {      // round 2: launch bounds of the short-series / 28-tap group variants
+        {
+            Bufs b; b.alloc(28416, 128, 0.72, 100);
+            rung<16, 28, 8, 16, 4, 3>("G8 R16 K28 M3 (T=128)", b, 100, true);
+            rung<16, 28, 8, 16, 4, 2>("G8 R16 K28 M2 (T=128)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 190, 0.72, 100);
+            rung<24, 28, 8, 24, 4, 3>("G8 R24 K28 M3 (T=190)", b, 100, true);
+            rung<24, 28, 8, 24, 4, 2>("G8 R24 K28 M2 (T=190)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(21312, 240, 0.75, 100);
+            rung<15, 28, 16, 8, 4, 3>("G16 R15 K28 M3 (T=240)", b, 100, true);
+            rung<15, 28, 16, 8, 4, 2>("G16 R15 K28 M2 (T=240)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(21312, 300, 0.72, 100);
+            rung<19, 28, 16, 19, 4, 3>("G16 R19 K28 M3 (T=300)", b, 100, true);
+            rung<19, 28, 16, 19, 4, 2>("G16 R19 K28 M2 (T=300)", b, 100);
+            b.free_all();
+        }
     } else if (set == 2) {
         Bufs b; b.alloc(16000, 600, 1.0, 100);
         run32<20, 20, true, 4, 3>("G32 R20 K20 circ W4 M3 (ref)", b, 100, true);
