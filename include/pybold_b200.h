@@ -161,6 +161,21 @@ int pb_bd_f64(const double *y, double t_r, double hrf_dur,
               double *out_J, double *out_r, double *out_g, int32_t *out_ntrace,
               int64_t V, int T, int K, pb_stream_t stream);
 
+/* Same solve for a SUBSET of the batch: voxels with active[v] == 0 are skipped and their output rows stay
+ * untouched; out_J may be NULL (no cost trace).  This is the inner loop of `deconv(lbda=None)`
+ * (pybold/bold_signal.py:114-138), which the outer lambda loop calls again and again, warm-started through
+ * w0, while more and more voxels have met their stopping rule. */
+int pb_deconv_masked_f32(const float *y, const float *h, int64_t h_stride, const float *L, int64_t L_stride,
+                         const float *lbda, int64_t lbda_stride, const float *w0, const unsigned char *active,
+                         int nb_iter, int early_stopping, int wind, double tol, float *out_x, float *out_z,
+                         float *out_dz, float *out_J, int32_t *out_niter, int64_t V, int T, int K,
+                         pb_stream_t stream);
+int pb_deconv_masked_f64(const double *y, const double *h, int64_t h_stride, const double *L, int64_t L_stride,
+                         const double *lbda, int64_t lbda_stride, const double *w0, const unsigned char *active,
+                         int nb_iter, int early_stopping, int wind, double tol, double *out_x, double *out_z,
+                         double *out_dz, double *out_J, int32_t *out_niter, int64_t V, int T, int K,
+                         pb_stream_t stream);
+
 /* ---- cfg5: regularisation path, `deconv` (fixed lambda, no early stopping, pybold/bold_signal.py:49-97)
  * for every lambda of lbdas[n_lbda] and every voxel of y[V,T] in one launch -- the lambda grid search of
  * examples/icassp_2019/validation.py batched over (lambda, voxel).  Problem (l, v) reads row v of y (the

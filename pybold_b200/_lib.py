@@ -51,6 +51,8 @@ _OPS = {
     "pb_lipschitz_frob": [_P, c_int64, _P, c_int64, c_int, c_int, _P],
     "pb_deconv": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_double,
                   _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P],
+    "pb_deconv_masked": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int, c_double,
+                         _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P],
     "pb_deconv_lbda_path": [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P],
     "pb_bd": [_P, c_double, c_double, _P, c_int64, _P, c_int64, _P, c_double, c_double,
               c_int, c_int, c_int, c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P,

@@ -35,12 +35,14 @@ def _as_batch(y, dtype):
 
 
 def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e-6, wind=6,
-                 nb_iter=1000, events=None):
+                 nb_iter=1000, events=None, active=None, out=None, trace=True):
     """Device entry point: tensors in, tensors out.  Returns (x, z, diff_z, J_raw, n_iter).
 
     ``J_raw[v, k]`` is the un-normalised cost of iteration k (NaN past ``n_iter[v]``);
     ``lipschitz`` is the constant actually used (0.9 x power estimate in ``deconv``).
     ``events=(e0, e1)``: CUDA events recorded immediately around the solver launch (benchmarks).
+    ``active`` (uint8 ``[V]``): voxels with 0 are skipped, their rows of the outputs stay as they are;
+    ``out=(x, z, diff_z, n_iter)`` reuses output tensors; ``trace=False`` skips the cost trace (J is None).
     """
     V, T = y.shape
     dtype, dev = y.dtype, y.device
@@ -57,18 +59,32 @@ def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e
     y = y.contiguous()
     lb, lb_stride = per_voxel(lbda, V, dtype, dev, "lbda")
     Lc, L_stride = per_voxel(lipschitz, V, dtype, dev, "lipschitz")
-    x = torch.empty_like(y)
-    z = torch.empty_like(y)
-    dz = torch.empty_like(y)
-    J = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
-    n_iter = torch.zeros(V, dtype=torch.int32, device=dev)
+    if out is not None:
+        x, z, dz, n_iter = out
+        for t in (x, z, dz):
+            if tuple(t.shape) != (V, T) or t.dtype != dtype or t.device != dev or not t.is_contiguous():
+                raise ValueError("out tensors must be contiguous %s tensors of shape (%d, %d) on %s" % (dtype, V, T, dev))
+    else:
+        x = torch.empty_like(y)
+        z = torch.empty_like(y)
+        dz = torch.empty_like(y)
+        n_iter = torch.zeros(V, dtype=torch.int32, device=dev)
+    J = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev) if trace else None
+    if active is not None and (active.dtype != torch.uint8 or active.numel() != V or active.device != dev):
+        raise ValueError("active must be a uint8 tensor with one entry per voxel on %s" % dev)
     with torch.cuda.device(dev):        # the C side sizes its grid for, and launches on, the current device
         if events is not None:
             events[0].record()
-        rc = _lib.fn("pb_deconv", dtype)(
-            ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0),
-            int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
-            ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
+        if active is None and trace:
+            rc = _lib.fn("pb_deconv", dtype)(
+                ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0),
+                int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
+                ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
+        else:
+            rc = _lib.fn("pb_deconv_masked", dtype)(
+                ptr(y), ptr(hrf), h_stride, ptr(Lc), L_stride, ptr(lb), lb_stride, ptr(w0), ptr(active),
+                int(nb_iter), int(bool(early_stopping)), int(wind), float(tol),
+                ptr(x), ptr(z), ptr(dz), ptr(J), ptr(n_iter), V, T, K, stream_ptr())
         if events is not None:
             events[1].record()
     _lib.check(rc, "pb_deconv")

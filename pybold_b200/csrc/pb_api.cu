@@ -367,7 +367,7 @@ int run_toeplitz(const real *k, int klen, real *out, int64_t dim_out, int64_t di
 template <typename real>
 int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
     if (a.V == 0) return PB_OK;
-    if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz || !a.out_J ||
+    if (!a.y || !a.h || !a.L || !a.lbda || !a.out_x || !a.out_z || !a.out_dz ||
         !a.out_niter || a.V < 0 || a.T <= 0 || a.K <= 0 || a.nb_iter < 1 || a.wind < 0)
         return PB_ERR_INVALID_ARG;
     if (a.T > PB_MAX_T || a.K > PB_MAX_K || a.nb_iter > PB_MAX_ITER) return PB_ERR_UNSUPPORTED;
@@ -645,6 +645,20 @@ int pb_hrf_len_ex(double t_r, double dur, double dt) {
         a.early_stopping = early_stopping; a.wind = wind; a.tol = tol; a.out_x = out_x;                \
         a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J; a.out_niter = out_niter; a.V = V;         \
         a.T = T; a.K = K;                                                                              \
+        if (!out_J) return PB_ERR_INVALID_ARG;                                                         \
+        return run_deconv<REAL>(a, s);                                                                 \
+    }                                                                                                  \
+    int pb_deconv_masked_##SUF(const REAL *y, const REAL *h, int64_t h_stride, const REAL *L,          \
+                               int64_t L_stride, const REAL *lbda, int64_t lbda_stride, const REAL *w0, \
+                               const unsigned char *active, int nb_iter, int early_stopping, int wind,  \
+                               double tol, REAL *out_x, REAL *out_z, REAL *out_dz, REAL *out_J,         \
+                               int32_t *out_niter, int64_t V, int T, int K, pb_stream_t s) {            \
+        pb::DeconvArgs<REAL> a;                                                                        \
+        a.y = y; a.h = h; a.h_stride = h_stride; a.L = L; a.L_stride = L_stride; a.lbda = lbda;        \
+        a.lbda_stride = lbda_stride; a.w0 = w0; a.nb_iter = nb_iter;                                   \
+        a.early_stopping = early_stopping; a.wind = wind; a.tol = tol; a.out_x = out_x;                \
+        a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J; a.out_niter = out_niter; a.V = V;         \
+        a.T = T; a.K = K; a.active = active;                                                           \
         return run_deconv<REAL>(a, s);                                                                 \
     }                                                                                                  \
     int pb_deconv_lbda_path_##SUF(const REAL *y, const REAL *h, const REAL *L, const REAL *lbdas,      \

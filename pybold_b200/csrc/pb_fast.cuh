@@ -267,6 +267,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
     WarpVoxel<real, R, KMAX, CIRC> vx;
     vx.init(lane, T);
     for (int64_t v = (int64_t)blockIdx.x * WARPS + warp; v < p.V; v += (int64_t)gridDim.x * WARPS) {
+        if (!p.is_active(v)) continue;
         const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
         vx.set_dy(yv, T);
@@ -288,7 +289,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
             if (k > 0) {   // cost of the previous iterate: its residual has just been formed
                 const double J = 0.5 * warp_sum((double)vx.partial_sumsq(res)) +
                                  lam * warp_sum((double)vx.partial_sumabs(vx.w));
-                if (lane == 0) Jv[k - 1] = (real)J;
+                if (lane == 0 && p.out_J) Jv[k - 1] = (real)J;
             }
             real g[R], u[R], pc, pw;
             vx.adjoint(res, g);
@@ -338,7 +339,7 @@ fast_deconv_kernel(DeconvArgs<real> p, int ring_rows) {
         if (n_done > 0) {
             const double J = 0.5 * warp_sum((double)vx.partial_sumsq(res)) +
                              lam * warp_sum((double)vx.partial_sumabs(vx.w));
-            if (lane == 0) Jv[n_done - 1] = (real)J;
+            if (lane == 0 && p.out_J) Jv[n_done - 1] = (real)J;
         }
         real y[R], z[R];
         vx.load_y(yv, T, y);

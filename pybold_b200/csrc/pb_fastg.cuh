@@ -695,7 +695,8 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
     const int q = vx.q;
     for (int64_t v0 = ((int64_t)blockIdx.x * WARPS + warp) * VPW; v0 < p.V;
          v0 += (int64_t)gridDim.x * WARPS * VPW) {
-        const bool on = v0 + grp < p.V;
+        const bool on = v0 + grp < p.V && p.is_active(v0 + grp < p.V ? v0 + grp : p.V - 1);
+        if (!__any_sync(PB_FULL, on)) continue;
         const int64_t v = on ? v0 + grp : p.V - 1;
         const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
@@ -712,13 +713,14 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
         const bool writer = on && q == 0;
+        const bool tracer = writer && p.out_J;
         real res[R];
         for (int k = 0; k < p.nb_iter; ++k) {
             vx.forward(res);
             if (k > 0) {
                 const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
                                  lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-                if (writer) Jv[k - 1] = (real)J;
+                if (tracer) Jv[k - 1] = (real)J;
             }
             real g[R];
             vx.adjoint(res, g);
@@ -728,7 +730,7 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
         {
             const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
                              lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-            if (writer) Jv[p.nb_iter - 1] = (real)J;
+            if (tracer) Jv[p.nb_iter - 1] = (real)J;
         }
         real y[R], z[R];
         vx.load_y(yv, T, y);
@@ -802,7 +804,11 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
     for (;;) {
         if (__any_sync(PB_FULL, want)) {
             unsigned int idx = 0xffffffffu;
-            if (want && q == 0) idx = atomicAdd(p.queue, 1u);
+            if (want && q == 0) {
+                do {                                    // skip the problems masked out by p.active
+                    idx = atomicAdd(p.queue, 1u);
+                } while ((int64_t)idx < p.V && !p.is_active(idx));
+            }
             idx = __shfl_sync(PB_FULL, idx, 0, G);
             if (want) {
                 want = false;
@@ -835,7 +841,7 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
             // number of iterations done and this is its last cost.
             const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
                              lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-            if (active && q == 0 && k > 0) Jv[k - 1] = (real)J;
+            if (active && q == 0 && k > 0 && p.out_J) Jv[k - 1] = (real)J;
         }
         if (__any_sync(PB_FULL, closing)) {
             // A voxel that stopped in the previous turn: the residual of its final iterate is the one just

@@ -215,6 +215,10 @@ struct DeconvArgs {
     int64_t y_mod = 0, lbda_div = 0;
     // early-stopping group kernel: device counter (zeroed on the launch stream) the groups pull voxels from
     unsigned int *queue = nullptr;
+    // optional mask: problems with active[v] == 0 are skipped, their outputs stay untouched (the outer loop
+    // of deconv(lbda=None) keeps calling with fewer and fewer live voxels); out_J may be null (no cost trace)
+    const unsigned char *active = nullptr;
+    __device__ __forceinline__ bool is_active(int64_t v) const { return !active || active[v] != 0; }
     __device__ __forceinline__ const real *y_row(int64_t v) const { return y + (y_mod ? v % y_mod : v) * T; }
     __device__ __forceinline__ double lam_of(int64_t v) const {
         return (double)lbda[lbda_div ? v / lbda_div : v * lbda_stride];
@@ -236,6 +240,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
     const int sub = p.wind / 2, nring = p.wind - 1;
 
     for (int64_t v = (int64_t)blockIdx.x * nwarp + warp; v < p.V; v += (int64_t)gridDim.x * nwarp) {
+        if (!p.is_active(v)) continue;
         const real *yv = p.y_row(v);
         const real *hv = p.h + v * p.h_stride;
         for (int i = lane; i < T; i += 32) {
@@ -253,7 +258,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
             g.forward();
             if (k > 0) {
                 const double J = 0.5 * g.sumsq(g.bs) + lam * g.sumabs(g.ws);
-                if (lane == 0) Jv[k - 1] = (real)J;
+                if (lane == 0 && p.out_J) Jv[k - 1] = (real)J;
             }
             g.adjoint();
             double d0, d1;
@@ -284,7 +289,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
         g.forward();
         if (n_done > 0) {
             const double J = 0.5 * g.sumsq(g.bs) + lam * g.sumabs(g.ws);
-            if (lane == 0) Jv[n_done - 1] = (real)J;
+            if (lane == 0 && p.out_J) Jv[n_done - 1] = (real)J;
         }
         for (int i = lane; i < T; i += 32) {
             p.out_x[v * T + i] = g.bs[i] + g.ys[i];

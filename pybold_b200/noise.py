@@ -62,6 +62,13 @@ def mad_daub_noise_est(x, c=0.6744):
 
 def deconv_auto_lbda(y_in, yb, one_d, hrf, lipschitz, sigma, early_stopping, tol, wind,
                      nb_iter, nb_sub_iter):
+    """Outer loop of ``deconv(lbda=None)`` (pybold/bold_signal.py:99-214) for a batch.
+
+    Every outer iteration is two launches: the inner prox-gradient loops of the voxels that are still
+    running (``pb_deconv_masked``: warm start, no cost trace, finished voxels skipped) and the fused
+    residual / alpha / lambda update (``pb_noise_step``).  The alpha-window stop of every voxel is
+    evaluated on the device; the host only looks at "is anything still running" every few iterations.
+    """
     from .bold_signal import deconv_batch
     V, T = yb.shape
     dtype, dev = yb.dtype, yb.device
@@ -74,39 +81,49 @@ def deconv_auto_lbda(y_in, yb, one_d, hrf, lipschitz, sigma, early_stopping, tol
     w = torch.zeros_like(yb)
     x = torch.zeros_like(yb)
     z = torch.zeros_like(yb)
+    scratch = (torch.empty_like(yb), torch.empty_like(yb), torch.empty_like(yb),
+               torch.zeros(V, dtype=torch.int32, device=dev))
     active = torch.ones(V, dtype=torch.uint8, device=dev)
+    n_outer = torch.full((V,), nb_iter, dtype=torch.int64, device=dev)   # outer iterations each voxel runs
     sub = int(wind / 2)
     hist = []
-    J, R, G = [], [], []
+    J = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
+    R = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
+    G = torch.full((V, nb_iter), float("nan"), dtype=dtype, device=dev)
     step = _lib.fn("pb_noise_step", dtype)
+    check_every = 1 if V == 1 else 4
     for i in range(nb_iter):
         x_n, z_n, w_n, _, _ = deconv_batch(yb, hrf, lbda, lipschitz, w, early_stopping, tol, wind,
-                                           nb_sub_iter)
+                                           nb_sub_iter, active=active, out=scratch, trace=False)
         r = torch.empty(V, dtype=dtype, device=dev)
         g = torch.empty(V, dtype=dtype, device=dev)
         # bold_signal.py:139-145: keep the result of the active voxels, r, g, alpha and lambda updates
-        rc = step(ptr(x_n), ptr(z_n), ptr(w_n), ptr(yb), ptr(sigma), ptr(active), mu, ptr(x), ptr(z), ptr(w),
-                  ptr(alpha), ptr(lbda), ptr(r), ptr(g), V, T, stream_ptr())
+        with torch.cuda.device(dev):
+            rc = step(ptr(x_n), ptr(z_n), ptr(w_n), ptr(yb), ptr(sigma), ptr(active), mu, ptr(x), ptr(z), ptr(w),
+                      ptr(alpha), ptr(lbda), ptr(r), ptr(g), V, T, stream_ptr())
         _lib.check(rc, "pb_noise_step")
         hist.append(alpha.clone())
         if len(hist) > wind:
             hist = hist[1:]
-        R.append(r)
-        G.append(g)
-        J.append(0.5 * r + lbda * g)
+        live = active.bool()
+        R[:, i] = torch.where(live, r, R[:, i])
+        G[:, i] = torch.where(live, g, G[:, i])
+        J[:, i] = torch.where(live, 0.5 * r + lbda * g, J[:, i])
         if early_stopping and i > wind and sub > 0:                 # bold_signal.py:164-178
             old_it = torch.stack(hist[:-sub]).mean(dim=0)
             new_it = torch.stack(hist[-sub:]).mean(dim=0)
-            stop = (new_it - old_it).abs() / new_it.abs() < tol
+            stop = ((new_it - old_it).abs() / new_it.abs() < tol) & live
+            n_outer = torch.where(stop, torch.full_like(n_outer, i + 1), n_outer)
             active = active & (~stop).to(torch.uint8)
-            if not bool(active.any()):
+            if (i % check_every == 0 or i == nb_iter - 1) and not bool(active.any()):
                 break
-    # bold_signal.py:180-212: last deconvolution with the final lambda
-    x, z, w, _, _ = deconv_batch(yb, hrf, lbda, lipschitz, w, early_stopping, tol, wind, nb_sub_iter)
-    J, R, G = torch.stack(J, 1), torch.stack(R, 1), torch.stack(G, 1)
+    # bold_signal.py:180-212: last deconvolution with the final lambda, every voxel
+    x, z, w, _, _ = deconv_batch(yb, hrf, lbda, lipschitz, w, early_stopping, tol, wind, nb_sub_iter, trace=False)
     if one_d:
+        n = int(n_outer[0])
         conv = lambda t: like_input(t[0], y_in)  # noqa: E731
-        return (conv(x), conv(z), conv(w), [float(v) for v in J[0]], [float(v) for v in R[0]],
-                [float(v) for v in G[0]])
+        return (conv(x), conv(z), conv(w), [float(v) for v in J[0, :n]], [float(v) for v in R[0, :n]],
+                [float(v) for v in G[0, :n]])
+    n_max = int(n_outer.max())
     conv = lambda t: like_input(t, y_in)  # noqa: E731
-    return conv(x), conv(z), conv(w), conv(J), conv(R), conv(G)
+    return conv(x), conv(z), conv(w), conv(J[:, :n_max]), conv(R[:, :n_max]), conv(G[:, :n_max])

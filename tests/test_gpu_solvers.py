@@ -433,9 +433,22 @@ def test_deconv_auto_lambda_vs_reference_golden(golden):
         assert rel(x, g["x_" + tag]) < 1e-9, tag
         assert rel(J, g["J_" + tag]) < 1e-9 and rel(R, g["R_" + tag]) < 1e-9, tag
         assert rel(G, g["G_" + tag]) < 1e-9, tag
-    # the batched call gives every voxel its own stop iteration
-    tags = ["b", "e"]                                       # same y, h; different sigma / tol / wind
-    assert np.array_equal(g["y_b"], g["y_e"])
+    # batched: every voxel gets its own outer stop iteration (masked inner solves once a voxel has stopped)
+    # and the same numbers as when it is solved alone
+    tag = "b"
+    kw = dict(lbda=None, early_stopping=True, tol=float(g["tol_b"]), wind=int(g["wind_b"]),
+              nb_iter=int(g["nb_iter_b"]), nb_sub_iter=int(g["nb_sub_iter_b"]), x0=g["x0_b"])
+    sig = np.array([0.5, 0.25, 1.0, 0.5])
+    yb = np.stack([g["y_b"], g["y_b"], g["y_b"], g["y_a"]])
+    xb, zb, dzb, Jb, Rb, Gb = pb.deconv(yb, 1.0, g["h_b"], sigma=sig, **kw)
+    n_stop = []
+    for v in range(4):
+        x1, z1, dz1, J1, R1, G1 = pb.deconv(yb[v], 1.0, g["h_b"], sigma=float(sig[v]), **kw)
+        n_stop.append(len(J1))
+        assert np.array_equal(zb[v], z1) and np.array_equal(dzb[v], dz1) and np.array_equal(xb[v], x1), v
+        assert np.array_equal(Jb[v, :len(J1)], np.array(J1)) and np.all(np.isnan(Jb[v, len(J1):])), v
+        assert np.array_equal(Rb[v, :len(J1)], np.array(R1)) and np.array_equal(Gb[v, :len(J1)], np.array(G1)), v
+    assert n_stop[0] == len(g["J_b"]) and len(set(n_stop)) > 1 and Jb.shape[1] == max(n_stop)
 
 
 def test_hrf_estim_vs_reference_golden(golden):
