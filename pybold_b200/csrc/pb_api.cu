@@ -645,7 +645,7 @@ int pb_hrf_len_ex(double t_r, double dur, double dt) {
         a.early_stopping = early_stopping; a.wind = wind; a.tol = tol; a.out_x = out_x;                \
         a.out_z = out_z; a.out_dz = out_dz; a.out_J = out_J; a.out_niter = out_niter; a.V = V;         \
         a.T = T; a.K = K;                                                                              \
-        if (!out_J) return PB_ERR_INVALID_ARG;                                                         \
+        if (!out_J && V != 0) return PB_ERR_INVALID_ARG;                                               \
         return run_deconv<REAL>(a, s);                                                                 \
     }                                                                                                  \
     int pb_deconv_masked_##SUF(const REAL *y, const REAL *h, int64_t h_stride, const REAL *L,          \

@@ -128,6 +128,15 @@ int main(int argc, char **argv) {
         rung<20, 20, 16, 8, 4, 3, 0, 2>("G16 R20 SMH2 M3", b, 100);
         rung<20, 20, 16, 8, 4, 4, 1, 2>("G16 R20 SMH2 LEAN1 M4", b, 100);
         b.free_all();
+    } else if (set == 7) {      // round 2: four CTAs per SM (16 warps) without the shared-memory halo buffers
+        Bufs b; b.alloc(42624, 300, 1.0, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 M3 (12 warps)", b, 100, true);
+        rung<19, 20, 16, 8, 4, 4>("G16 R19 M4 plain", b, 100);
+        rung<19, 20, 16, 8, 4, 4, 2, 0>("G16 R19 M4 LEAN2 (dy in smem)", b, 100);
+        rung<19, 20, 16, 8, 4, 4, 1, 0>("G16 R19 M4 LEAN1 (dy, taps in smem)", b, 100);
+        rung<19, 20, 16, 8, 2, 8, 2, 0>("G16 R19 W2 M8 LEAN2", b, 100);
+        rung<19, 20, 16, 8, 4, 5, 1, 0>("G16 R19 M5 LEAN1 (20 warps)", b, 100);
+        b.free_all();
     } else if (set == 6) {      // round 2: launch bounds of the short-series / 28-tap group variants
         {
             Bufs b; b.alloc(28416, 128, 0.72, 100);
