@@ -16,13 +16,14 @@ def spectral_radius_est(L, x_shape, nb_iter=30, tol=1.0e-6, verbose=False, x0=No
 
     Like the reference, the start vector is drawn from NumPy's *global* generator
     (``np.random.randn(*x_shape)``) unless ``x0`` is given, so seeding ``np.random`` the same
-    way gives the same estimate.  ``L`` must be ``ConvAndLinear(DiscretInteg(), kernel, T)``:
-    the whole iteration then runs in one kernel.  ``x0`` / the kernel may be batched ``[V, .]``.
+    way gives the same estimate.  For ``L = ConvAndLinear(DiscretInteg(), kernel, T)`` -- what ``deconv``
+    builds -- the whole iteration runs in ONE kernel (``x0`` / the kernel may be batched ``[V, .]``); any
+    other object with ``op`` / ``adj`` is iterated call by call like the reference does.
     """
-    if not (isinstance(L, ConvAndLinear) and isinstance(L.M, DiscretInteg)):
-        raise NotImplementedError("spectral_radius_est runs on ConvAndLinear(DiscretInteg(), ...) only")
     if x0 is None:
         x0 = np.random.randn(*x_shape)
+    if not (isinstance(L, ConvAndLinear) and isinstance(L.M, DiscretInteg)):
+        return _power_iteration_generic(L, x0, nb_iter, tol, verbose)
     dtype = pick_dtype(L.k, x0)
     xd = to_device(x0, dtype)
     kd = to_device(L.k, dtype)
@@ -39,6 +40,28 @@ def spectral_radius_est(L, x_shape, nb_iter=30, tol=1.0e-6, verbose=False, x0=No
     if scalar:
         return float(out[0])
     return out if isinstance(x0, torch.Tensor) else out.cpu().numpy()
+
+
+def _power_iteration_generic(L, x0, nb_iter, tol, verbose):
+    """pybold/utils.py:94-109 for ANY object with ``op`` / ``adj`` (the reference's duck-typed operator
+    protocol): the loop of the reference, statement by statement, around the operator's own calls.  With the
+    operators of ``pybold_b200.linear`` every ``op`` / ``adj`` is a device kernel; the two norms per step are
+    the only arithmetic done here."""
+    def norm(a):
+        if isinstance(a, torch.Tensor):
+            return float(torch.linalg.vector_norm(a.double()))
+        return float(np.linalg.norm(np.asarray(a, dtype=np.float64)))
+
+    x_old = x0
+    x_new = x_old
+    for i in range(nb_iter):
+        x_new = L.adj(L.op(x_old)) / norm(x_old)
+        if abs(norm(x_new) - norm(x_old)) < tol:
+            if verbose:
+                print("Spectral radius estimation converged at iteration {0}".format(i))
+            break
+        x_old = x_new
+    return norm(x_new)
 
 
 def _rows(x):

@@ -285,3 +285,28 @@ def test_spm_hrf_shape_parameters_vs_reference_golden(golden):
         assert np.array_equal(hb[v], h1)
     with pytest.raises(ValueError):
         pb.spm_hrf(1.0, p_disp=0.0)
+
+
+def test_spectral_radius_est_on_any_operator():
+    """utils.py:94-109 takes any object with op / adj: the integration operator alone (known largest singular
+    value of the T x T summation matrix) and a user-defined operator give the reference's numbers."""
+    import pybold_b200 as pb
+    from pybold_b200.utils import spectral_radius_est
+    T = 64
+    x0 = np.random.RandomState(4).randn(T)
+    got = spectral_radius_est(pb.DiscretInteg(), (T,), x0=x0, nb_iter=60)
+    Lmat = np.tril(np.ones((T, T)))
+
+    class Dense:
+        def op(self, x):
+            return Lmat.dot(x)
+
+        def adj(self, x):
+            return Lmat.T.dot(x)
+    want = orc.spectral_radius_est(Dense(), x0, nb_iter=60)
+    assert abs(got / want - 1) < 1e-12
+    assert abs(spectral_radius_est(Dense(), (T,), x0=x0, nb_iter=60) / want - 1) < 1e-14
+    np.random.seed(5)
+    a = spectral_radius_est(pb.DiscretInteg(), (T,))
+    np.random.seed(5)
+    assert abs(a / orc.spectral_radius_est(Dense(), np.random.randn(T)) - 1) < 1e-12
