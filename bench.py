@@ -269,7 +269,6 @@ def main():
         return run_reference(args)
 
     from baseline import reference_runner as rr
-    rr.pin_threads()        # before NumPy: the joblib workers of the cpu_baseline leg inherit it
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -606,6 +605,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             from joblib import Parallel
+            rr.pin_threads()        # one BLAS / OpenMP thread per worker; the workers are spawned after this
             kind, fn = cpu_bd_runner()
             cores = min(os.cpu_count() or 1, 64)
             y_s = y_host[:cores * 5].numpy().astype(np.float64)

@@ -84,10 +84,19 @@ __device__ unsigned int pb_queue_pool[256];
 
 unsigned int *queue_slot() {
     static std::atomic<unsigned int> next{0};
-    unsigned int *base = nullptr;
-    if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), pb_queue_pool) != cudaSuccess) {
+    static std::atomic<unsigned int *> base_of[64];     // address of the pool on every device, looked up once
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
         cudaGetLastError();
         return nullptr;
+    }
+    unsigned int *base = base_of[dev].load(std::memory_order_acquire);
+    if (!base) {
+        if (cudaGetSymbolAddress(reinterpret_cast<void **>(&base), pb_queue_pool) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        base_of[dev].store(base, std::memory_order_release);
     }
     return base + (next.fetch_add(1u) & 255u);
 }
