@@ -79,8 +79,9 @@ int set_smem(K kernel, size_t bytes) {
 
 // Work-queue counters of the early-stopping kernels: the library owns no memory, so the
 // counters live in a small static device array; every launch takes the next slot round-robin and zeroes it
-// on its own stream, which keeps up to 256 launches in flight independent of each other.
-__device__ unsigned int pb_queue_pool[256];
+// on its own stream, which keeps up to 4096 launches in flight (on different streams) independent of each
+// other; launches on one stream are ordered anyway.
+__device__ unsigned int pb_queue_pool[4096];
 
 unsigned int *queue_slot() {
     static std::atomic<unsigned int> next{0};
@@ -98,7 +99,7 @@ unsigned int *queue_slot() {
         }
         base_of[dev].store(base, std::memory_order_release);
     }
-    return base + (next.fetch_add(1u) & 255u);
+    return base + (next.fetch_add(1u) & 4095u);
 }
 
 int last_error() {

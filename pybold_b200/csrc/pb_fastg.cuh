@@ -788,6 +788,7 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
     const int sub = p.wind / 2, nring = p.wind - 1;
     const real inv_old = real(1) / real(p.wind - sub), inv_new = real(1) / real(sub);
     const bool even_wind = p.wind - sub == sub;
+    const bool es_on = p.early_stopping != 0;
     GV vx;
     vx.init(lane, T);
     const int q = vx.q;
@@ -798,7 +799,7 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
     // per-group state (identical in the G lanes of a group)
     int64_t v = 0;
     int k = 0, ring_pos = 0;
-    bool active = false, want = true, closing = false;
+    bool active = false, want = true;
     double lam = 0.0;
     real step = 0, th = 0;
     for (;;) {
@@ -835,68 +836,20 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
         }
         if (!__any_sync(PB_FULL, active)) break;
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
-        real res[R];
-        vx.forward(res);
-        {   // cost of the previous iterate: its residual has just been formed.  For a closing voxel k is the
-            // number of iterations done and this is its last cost.
-            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
-                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
-            if (active && q == 0 && k > 0 && p.out_J) Jv[k - 1] = (real)J;
-        }
-        if (__any_sync(PB_FULL, closing)) {
-            // A voxel that stopped in the previous turn: the residual of its final iterate is the one just
-            // formed.  Store it and hand the group back to the queue; the neighbour group loses this
-            // turn's forward pass (its iterate is untouched), once per voxel.
-            real z[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
-            vx.scan_fwd(z);
-            if (closing) {
-                if (q == 0) p.out_niter[v] = k;
-                real y[R];
-                vx.load_y(p.y_row(v), T, y);
-#pragma unroll
-                for (int r = 0; r < R; ++r) y[r] += res[r];          // x = (A w - y) + y
-                vx.store(p.out_x + v * T, y, T, true);
-                vx.store(p.out_z + v * T, z, T, true);
-                vx.store(p.out_dz + v * T, vx.w, T, true);
-                closing = false;
-                active = false;
-                want = true;
-            }
-            continue;
-        }
-        real g[R], u[R];
-        vx.adjoint(res, g);
+        // ---- stop test of the iteration just done (reference iteration k - 1; Q5), evaluated at the START of
+        // the next turn: xx = [u_{k-wind+1}, ..., u_{k-1}, w_k] with w_k the iterate in registers.  Its long
+        // dependent tail (window sums -> norms -> segmented sums -> one square root -> vote) sits in the same
+        // basic block as the forward pass below and overlaps with its FFMA.  Always computed (the first turns
+        // read an unfilled ring and are ignored).
+        real qn[4] = {0, 0, 0, 0}, qd[4] = {0, 0, 0, 0};
         {
-            const real ob = real(1) + beta[k];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                u[r] = fma(-step, g[r], vx.w[r]);
-                const real cl = fmin(fmax(u[r], -th), th);
-                vx.w[r] = fma(-ob, cl, u[r]);
-            }
-        }
-        {   // u_k into the ring slot k % nring
-            real *slot = ring + (size_t)ring_pos * 32 * RP;
-#pragma unroll
-            for (int c = 0; c < NV; ++c) {
-                V4 t;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) t.t[e] = u[4 * c + e < R ? 4 * c + e : R - 1];
-                reinterpret_cast<V4 *>(slot)[c] = t;
-            }
-        }
-        // xx = [u_{k-wind+2}, ..., u_k, w_k]; old = mean(first wind - sub), new = mean(last sub)
-        bool stop = false;
-        if (__any_sync(PB_FULL, active && k > p.wind)) {
             real so[R], sn[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 so[r] = 0;
                 sn[r] = vx.w[r];
             }
-            int pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;       // oldest u of this group's window
+            int pos = ring_pos;                                        // oldest u of this group's window
             auto add_slot = [&](real (&acc)[R]) {
                 const real *slot = ring + (size_t)pos * 32 * RP;
                 pos = pos + 1 == nring ? 0 : pos + 1;
@@ -910,34 +863,87 @@ fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
             };
             for (int m = 0; m < p.wind - sub; ++m) add_slot(so);
             for (int m = p.wind - sub; m < p.wind - 1; ++m) add_slot(sn);
-            real qn = 0, qd = 0;
             if (even_wind) {
                 // both means are over wind / 2 entries: the common factor 1 / sub is applied to the norms
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const real df = sn[r] - so[r];
-                    qn = fma(df, df, qn);
-                    qd = fma(sn[r], sn[r], qd);
+                    qn[r & 3] = fma(df, df, qn[r & 3]);
+                    qd[r & 3] = fma(sn[r], sn[r], qd[r & 3]);
                 }
             } else {
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     const real mo = so[r] * inv_old, mn = sn[r] * inv_new;
-                    qn = fma(mn - mo, mn - mo, qn);
-                    qd = fma(mn, mn, qd);
+                    qn[r & 3] = fma(mn - mo, mn - mo, qn[r & 3]);
+                    qd[r & 3] = fma(mn, mn, qd[r & 3]);
                 }
             }
+        }
+        real res[R];
+        vx.forward(res);
+        bool stop;
+        {
             const double scale = even_wind ? (double)inv_new * (double)inv_new : 1.0;
-            const double pn = scale * (double)Seg<real, G>::sum(qn);
-            const double pd = scale * (double)Seg<real, G>::sum(qd);
+            const double pn = scale * (double)Seg<real, G>::sum((qn[0] + qn[1]) + (qn[2] + qn[3]));
+            const double pd = scale * (double)Seg<real, G>::sum((qd[0] + qd[1]) + (qd[2] + qd[3]));
             // ||new - old|| / (||new|| + 1e-10) < tol  <=>  pn < (tol (sqrt(pd) + 1e-10))^2, with the one
             // square root from a float estimate refined in double (no FP64 sqrt / division sequences)
             const double rhs = p.tol * (sqrt_refined(pd) + 1.0e-10);
-            stop = k > p.wind && pn < rhs * rhs;
+            stop = es_on && k - 1 > p.wind && pn < rhs * rhs;
         }
-        closing = active && (stop || k + 1 == p.nb_iter);
+        {   // cost of the previous iterate: its residual has just been formed.  For a closing voxel k is the
+            // number of iterations done and this is its last cost.
+            const double J = 0.5 * (double)Seg<real, G>::sum(vx.partial_sumsq(res)) +
+                             lam * (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
+            if (active && q == 0 && k > 0 && p.out_J) Jv[k - 1] = (real)J;
+        }
+        const bool closing = active && k > 0 && (stop || k == p.nb_iter);
+        if (__any_sync(PB_FULL, closing)) {
+            // The iterate in registers is final for this voxel and the residual just formed is its own: store
+            // it and hand the group back to the queue; the neighbour group loses this turn's forward pass
+            // (its iterate is untouched), once per voxel.
+            real z[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[r] = vx.w[r];
+            vx.scan_fwd(z);
+            if (closing) {
+                if (q == 0) p.out_niter[v] = k;
+                real y[R];
+                vx.load_y(p.y_row(v), T, y);
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[r] += res[r];          // x = (A w - y) + y
+                vx.store(p.out_x + v * T, y, T, true);
+                vx.store(p.out_z + v * T, z, T, true);
+                vx.store(p.out_dz + v * T, vx.w, T, true);
+                active = false;
+                want = true;
+            }
+            continue;
+        }
+        real g[R], u[R];
+        vx.adjoint(res, g);
+        {
+            const real ob = real(1) + beta[k < p.nb_iter ? k : p.nb_iter - 1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                u[r] = fma(-step, g[r], vx.w[r]);
+                const real cl = fmin(fmax(u[r], -th), th);
+                vx.w[r] = fma(-ob, cl, u[r]);
+            }
+        }
+        {   // u_k into the ring slot k % nring; afterwards ring_pos points at the oldest entry again
+            real *slot = ring + (size_t)ring_pos * 32 * RP;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                V4 t;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t.t[e] = u[4 * c + e < R ? 4 * c + e : R - 1];
+                reinterpret_cast<V4 *>(slot)[c] = t;
+            }
+        }
         // k = iterations done; groups without a voxel iterate on stale registers, keep their indices in range
-        k = k + 1 < p.nb_iter || closing ? k + 1 : p.nb_iter - 1;
+        k = k < p.nb_iter ? k + 1 : k;
         ring_pos = ring_pos + 1 == nring ? 0 : ring_pos + 1;
     }
 }
