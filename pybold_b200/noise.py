@@ -22,6 +22,9 @@ _DB3_DEC_HI = (-0.3326705529509569, 0.8068915093133388, -0.4598775021193313,
                -0.13501102001039084, 0.08544127388224149, 0.035226291882100656)
 
 
+_warned_sigma = False
+
+
 def _mad_rows(x, c, entry):
     dtype = pick_dtype(x)
     xd = to_device(x, dtype)
@@ -73,7 +76,16 @@ def deconv_auto_lbda(y_in, yb, one_d, hrf, lipschitz, sigma, early_stopping, tol
     V, T = yb.shape
     dtype, dev = yb.dtype, yb.device
     if sigma is None:
-        sigma = mad_daub_noise_est(yb)                               # bold_signal.py:103
+        # bold_signal.py:103.  The wavelet convention of this estimate could not be compared with PyWavelets
+        # itself (see mad_daub_noise_est): say so once, `sigma=` makes the run independent of it
+        global _warned_sigma
+        if not _warned_sigma:
+            import warnings
+            warnings.warn("pybold_b200.deconv(lbda=None): sigma comes from the on-device db3 MAD estimate, whose "
+                          "boundary convention is pinned on PyWavelets' documented examples only; pass sigma= for "
+                          "a run that does not depend on it", UserWarning, stacklevel=3)
+            _warned_sigma = True
+        sigma = mad_daub_noise_est(yb)
     sigma = torch.as_tensor(sigma, dtype=dtype, device=dev).reshape(-1).expand(V).clone()
     alpha = torch.ones(V, dtype=dtype, device=dev)                  # bold_signal.py:104
     lbda = 1.0 / (2.0 * alpha)
