@@ -60,7 +60,7 @@ GATHER_KEYS = {"all": ("x", "z", "diff_z", "h", "theta", "J", "r", "g"), "estima
                "none": ()}
 
 
-def config_dict(w, world, scaling, gather="all", overlap=True):
+def config_dict(w, world, scaling, gather="all", overlap=True, via="peer"):
     """Same keys and values in both arms (the driver compares them)."""
     V = w["voxels_per_gpu"]
     total = V * world if scaling == "weak" else V
@@ -72,10 +72,14 @@ def config_dict(w, world, scaling, gather="all", overlap=True):
             "t_r": w["t_r"], "hrf_dur": w["hrf_dur"], "nb_iter": w["nb_iter"], "lbda": w["lbda"],
             "theta_0": w["theta_0"], "bounds": list(w["bounds"]), "scaling": scaling,
             "partition": "contiguous voxel ranges over %d rank(s)" % world,
-            "gather": ("%s (%s) over NCCL after every step%s" % (
+            "gather": ("%s (%s) after every step%s" % (
                 gather, ", ".join(GATHER_KEYS[gather]),
                 ", on a side stream while the next step solves" if overlap and GATHER_KEYS[gather] else "")
                        if world > 1 else "single rank, nothing to gather"),
+            "gather_via": ("none" if world == 1 or not GATHER_KEYS[gather] else
+                           {"peer": "copy-engine writes into the peers' result tensors (CUDA IPC over NVLink), "
+                                    "one-element all-reduce as the fence",
+                            "nccl": "all_gather_into_tensor per output"}[via]),
             "l2": "GPU arm: L2 flushed between timed steps (256 MB write, excluded from the step time); "
                   "the working set of a step also exceeds the 126 MB L2"}
 
@@ -236,7 +240,7 @@ def run_reference(args):
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(w, args.gpus, args.scaling, args.gather, not args.no_overlap),
+        "config": config_dict(w, args.gpus, args.scaling, args.gather, not args.no_overlap, args.gather_via),
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": n_jobs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -259,6 +263,9 @@ def main():
     ap.add_argument("--nb-iter", type=int, default=WORKLOAD["nb_iter"])
     ap.add_argument("--gather", default="all", choices=["all", "estimates", "none"],
                     help="outputs gathered over NCCL after every step when N > 1")
+    ap.add_argument("--gather-via", default="peer", choices=["peer", "nccl"],
+                    help="peer: copy-engine writes into the peers' result tensors (CUDA IPC over NVLink) + a one-"
+                         "element all-reduce as the fence; nccl: all_gather_into_tensor per output")
     ap.add_argument("--no-overlap", action="store_true",
                     help="gather on the solver's stream instead of overlapping it with the next step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -276,7 +283,7 @@ def main():
     import pybold_b200 as pb
     from pybold_b200 import _lib
     from pybold_b200.bold_signal import bd_alloc, bd_batch, deconv_batch
-    from pybold_b200.sharding import ALL_OUTPUTS, gather_outputs, voxel_range
+    from pybold_b200.sharding import ALL_OUTPUTS, PeerGather, gather_outputs, voxel_range
     from pybold_b200.synth import gen_voxels_chunked, gen_voxels_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -291,7 +298,7 @@ def main():
     f32 = torch.float32
 
     w = dict(WORKLOAD, voxels_per_gpu=args.voxels, n_scans=args.scans, t_r=args.t_r, nb_iter=args.nb_iter)
-    cfg = config_dict(w, world, args.scaling, args.gather, not args.no_overlap)
+    cfg = config_dict(w, world, args.scaling, args.gather, not args.no_overlap, args.gather_via)
     T, n, K = w["n_scans"], w["nb_iter"], cfg["hrf_taps"]
     V_total = cfg["voxels_total"]
     lo, hi = voxel_range(V_total, rank, world)
@@ -388,9 +395,25 @@ def main():
         return bd_batch(y_dev, w["t_r"], lbda_dev, theta0_dev, None, w["hrf_dur"], [w["bounds"]],
                         n, False, 4, 1.0e-12, out=out_buf[b])
 
+    def out_spec(T_, K_, n_, dt):
+        return {"x": ((T_,), dt), "z": ((T_,), dt), "diff_z": ((T_,), dt), "h": ((K_,), dt), "theta": ((), dt),
+                "J": ((n_ + 2,), dt), "r": ((n_ + 2,), dt), "g": ((n_ + 2,), dt)}
+
+    peer = None
+    gather_via = args.gather_via if (world > 1 and keys) else "none"
+    if gather_via == "peer":
+        try:        # raises on every rank or on none
+            peer = [PeerGather({k: v for k, v in out_spec(T, K, n, f32).items() if k in keys}, V_total, dev)
+                    for _ in range(nbuf)]
+        except RuntimeError as exc:
+            peer, gather_via = None, "nccl (%s)" % exc
+
     def gather(out, b):
         if world > 1 and keys:   # final gather of the outputs; never inside the solve
-            gather_outputs(out, V_total, keys, into=gathered[b])
+            if peer is not None:
+                peer[b].gather(out, keys)
+            else:
+                gather_outputs(out, V_total, keys, into=gathered[b])
 
     warm = max(args.warmup, 3)
     for i in range(warm):
@@ -478,7 +501,7 @@ def main():
     extra = {}
     launches = args.steps
     if not args.no_extra:
-        del out_buf, y_dev, gathered
+        del out_buf, y_dev, gathered      # (the peer-gather tensors stay: other ranks hold IPC mappings of them)
         torch.cuda.empty_cache()
         x_steps, x_warm = 2, 1
 
@@ -496,9 +519,16 @@ def main():
             return bd_batch(y4, c4["t_r"], lbda_dev, theta0_dev, None, c4["hrf_dur"], [c4["bounds"]],
                             n4, False, 4, 1.0e-12, out=o4[b])
 
+        peer4 = None
+        if world > 1 and peer is not None:
+            peer4 = [PeerGather(out_spec(T4, K4, n4, f32), c4["voxels_total"], dev) for _ in range(nb4)]
+
         def gather4(out, b):
             if world > 1:
-                gather_outputs(out, c4["voxels_total"], ALL_OUTPUTS, into=g4[b])
+                if peer4 is not None:
+                    peer4[b].gather(out)
+                else:
+                    gather_outputs(out, c4["voxels_total"], ALL_OUTPUTS, into=g4[b])
 
         s_ms, k_ms, g_ms, _ = timed_steps(launch4, gather4, x_steps, x_warm, nb4)
         launches += x_steps
@@ -512,7 +542,7 @@ def main():
             "hrf_taps": K4, "nb_iter": n4, "data": "synthetic (device generator philox-v1, seed 4)",
             "roofline": fp32_roofline("bd", int(v4max), T4, K4, n4, k_ms,
                                       "variant %d" % _lib.lib.pb_solver_variant(T4, K4, 0))}
-        del y4, o4, g4
+        del y4, o4, g4, peer4
         torch.cuda.empty_cache()
 
         if world == 1:
@@ -625,6 +655,7 @@ def main():
             "config": cfg,
             "timing": {"solver_ms": kern_ms, "gather_ms": gath_ms,
                        "gather_exposed_ms": max(step_ms - kern_ms, 0.0), "gather_overlapped": nbuf > 1,
+                       "gather_path": gather_via,
                        "note": "CUDA events, max over ranks; solver_ms around the solver launch on its stream; "
                                "gather_ms around the NCCL calls on the stream they run on -- overlapped, they share "
                                "the GPU with the next step's solve and take longer than alone, what a step pays "
