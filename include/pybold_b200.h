@@ -261,6 +261,13 @@ int pb_noise_step_f64(const double *xn, const double *zn, const double *wn, cons
 int pb_transpose_f32(const float *in, float *out, int64_t rows, int64_t cols, pb_stream_t stream);
 int pb_transpose_f64(const double *in, double *out, int64_t rows, int64_t cols, pb_stream_t stream);
 
+/* ---- 8(e): one asynchronous copy between device buffers of this or of a PEER GPU (unified addressing:
+ * `dst` may be a CUDA-IPC mapping of another rank's result tensor).  A plain cudaMemcpyAsync on `stream`:
+ * the copy engines move the slab over NVLink while the SMs keep solving.  Used by the peer gather of
+ * pybold_b200/sharding.py; the reference gathers its per-voxel results by pickling them back from the
+ * joblib workers (examples/icassp_2019/validation.py:43-47). */
+int pb_copy_async(void *dst, const void *src, size_t bytes, pb_stream_t stream);
+
 /* ---- measurement utility (not part of the reference API) --------------------------------
  * FP32 FMA-pipe microbenchmark reported beside the nominal roofline: launches
  * `blocks` CTAs of 256 threads (use 4 per SM), each thread running 16 independent chains of

@@ -573,6 +573,13 @@ int pb_bench_fma_f32(float *sink, int blocks, int iters, pb_stream_t stream) {
 }
 
 
+int pb_copy_async(void *dst, const void *src, size_t bytes, pb_stream_t stream) {
+    if (bytes == 0) return PB_OK;
+    if (!dst || !src) return PB_ERR_INVALID_ARG;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    return e == cudaSuccess ? PB_OK : (int)e;
+}
+
 int pb_version(void) { return PB_VERSION; }
 int pb_max_T(void) { return PB_MAX_T; }
 int pb_max_K(void) { return PB_MAX_K; }

@@ -28,7 +28,7 @@ def _worker(rank, world, port, V, ret):
         torch.cuda.set_device(0)
         dev = torch.device("cuda", 0)
         spec = {"z": ((5,), torch.float32), "theta": ((), torch.float32), "J": ((3,), torch.float64)}
-        pg = PeerGather(spec, V, dev)
+        pg = PeerGather(spec, V, dev, mapping="ipc")
         lo, hi = voxel_range(V, rank, world)
         ok = True
         for rep in range(3):                                   # reused across steps
