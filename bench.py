@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--gather-via", default="peer", choices=["peer", "nccl"],
                     help="peer: copy-engine writes into the peers' result tensors (CUDA IPC over NVLink) + a one-"
                          "element all-reduce as the fence; nccl: all_gather_into_tensor per output")
+    ap.add_argument("--overlap-nccl", action="store_true",
+                    help="overlap the gather with the next step even on the NCCL path (measurement only)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="gather on the solver's stream instead of overlapping it with the next step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -387,18 +389,14 @@ def main():
     # ---- headline: device-resident inputs, reusable outputs: a step = one kernel launch (+ gather) ----
     lbda_dev = torch.full((1,), w["lbda"], dtype=f32, device=dev)
     theta0_dev = torch.full((1,), w["theta_0"], dtype=f32, device=dev)
-    nbuf = 2 if (world > 1 and keys and not args.no_overlap) else 1
-    out_buf = [bd_alloc(V, T, K, n, f32, dev) for _ in range(nbuf)]
-    gathered = [{} for _ in range(nbuf)]
-
-    def launch(b):
-        return bd_batch(y_dev, w["t_r"], lbda_dev, theta0_dev, None, w["hrf_dur"], [w["bounds"]],
-                        n, False, 4, 1.0e-12, out=out_buf[b])
-
     def out_spec(T_, K_, n_, dt):
         return {"x": ((T_,), dt), "z": ((T_,), dt), "diff_z": ((T_,), dt), "h": ((K_,), dt), "theta": ((), dt),
                 "J": ((n_ + 2,), dt), "r": ((n_ + 2,), dt), "g": ((n_ + 2,), dt)}
 
+    # The gather overlaps the next step only through the peer (copy-engine) path: an NCCL all-gather kernel on
+    # a side stream competes with the persistent solve for SMs and was measured 8.7 % slower per step on
+    # 8 GPUs than not overlapping at all (profiles/r02_scaling.txt); --overlap-nccl forces it for measurements.
+    nbuf = 2 if (world > 1 and keys and not args.no_overlap) else 1
     peer = None
     gather_via = args.gather_via if (world > 1 and keys) else "none"
     if gather_via == "peer":
@@ -407,6 +405,14 @@ def main():
                     for _ in range(nbuf)]
         except RuntimeError as exc:
             peer, gather_via = None, "nccl (%s)" % exc
+    if peer is None and not args.overlap_nccl:
+        nbuf = 1
+    out_buf = [bd_alloc(V, T, K, n, f32, dev) for _ in range(nbuf)]
+    gathered = [{} for _ in range(nbuf)]
+
+    def launch(b):
+        return bd_batch(y_dev, w["t_r"], lbda_dev, theta0_dev, None, w["hrf_dur"], [w["bounds"]],
+                        n, False, 4, 1.0e-12, out=out_buf[b])
 
     def gather(out, b):
         if world > 1 and keys:   # final gather of the outputs; never inside the solve
@@ -511,7 +517,7 @@ def main():
         lo4, hi4 = voxel_range(c4["voxels_total"], rank, world)
         V4, T4, n4 = hi4 - lo4, c4["n_scans"], c4["nb_iter"]
         y4 = gen_voxels_device(V4, T4, c4["t_r"], c4["hrf_dur"], seed=4, first_voxel=lo4, dtype=f32)
-        nb4 = 2 if (world > 1 and not args.no_overlap) else 1
+        nb4 = 2 if (world > 1 and not args.no_overlap and (peer is not None or args.overlap_nccl)) else 1
         o4 = [bd_alloc(V4, T4, K4, n4, f32, dev) for _ in range(nb4)]
         g4 = [{} for _ in range(nb4)]
 
@@ -657,9 +663,9 @@ def main():
                        "gather_exposed_ms": max(step_ms - kern_ms, 0.0), "gather_overlapped": nbuf > 1,
                        "gather_path": gather_via,
                        "note": "CUDA events, max over ranks; solver_ms around the solver launch on its stream; "
-                               "gather_ms around the NCCL calls on the stream they run on -- overlapped, they share "
-                               "the GPU with the next step's solve and take longer than alone, what a step pays "
-                               "is gather_exposed_ms = ms_per_step - solver_ms"},
+                               "gather_ms around the gather calls on the stream they run on -- overlapped, its fence "
+                               "only completes when the next solve lets a CTA in, what a step pays is "
+                               "gather_exposed_ms = ms_per_step - solver_ms"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
