@@ -310,3 +310,16 @@ def test_spectral_radius_est_on_any_operator():
     a = spectral_radius_est(pb.DiscretInteg(), (T,))
     np.random.seed(5)
     assert abs(a / orc.spectral_radius_est(Dense(), np.random.randn(T)) - 1) < 1e-12
+
+
+def test_layout_adapter_streams_host_matrices():
+    """Host [T, V] input in column chunks (pinned staging, two streams): same result as the one-shot path,
+    including a ragged last chunk, float64, a CPU tensor."""
+    from pybold_b200.io import voxels_from_timeseries
+    rng = np.random.RandomState(6)
+    a = rng.randn(300, 1000).astype(np.float32)
+    got = voxels_from_timeseries(a, chunk_voxels=256)            # 3 full chunks + 232 voxels
+    assert got.is_cuda and got.shape == (1000, 300) and np.array_equal(got.cpu().numpy(), a.T)
+    b = rng.randn(64, 513)
+    assert np.array_equal(voxels_from_timeseries(torch.from_numpy(b), chunk_voxels=128).cpu().numpy(), b.T)
+    assert np.array_equal(voxels_from_timeseries(a, chunk_voxels=4096).cpu().numpy(), a.T)    # one chunk: one-shot path
