@@ -45,7 +45,10 @@ GVARIANTS = [
     # 28-tap variants spill at 168 registers (measured +8 % at R = 16, +23 % at R = 24 with 255, round 2)
     ("float", R, 20, 8, R, 4, 3) for R in (10, 13, 16, 20, 24)
 ] + [
-    ("float", R, 28, 8, R, 4, 2) for R in (10, 13, 16, 20, 24)
+    # ... but with 28 taps the four double-precision scratch areas of a warp (8.5 KB per voxel) leave room for
+    # one CTA per SM only: two voxels per warp with few samples per lane are faster (measured, round 2:
+    # T = 96 +14 %, T = 128 +9 %, T = 190 +44 %; profiles/r02_exp_short_series.txt)
+    ("float", R, 28, 16, R, 4, 3) for R in (4, 6, 8, 10, 12)
 ]
 
 

@@ -998,8 +998,10 @@ int fast_deconvg_launch(const DeconvArgs<real> &a, cudaStream_t stream) {
 
 template <int R, int KMAX, int G, int TAIL>
 bool fastg_shape_ok(int T, int K) {
-    // G = 8 (four short series per warp, TAIL = R: every slot maskable) serves T down to half its slots
-    return K <= KMAX && T <= G * R && (G == 8 && TAIL == R ? 2 * T > G * R : G * R - T <= TAIL) && T >= 1;
+    // short-series variants (G = 8, or G = 16 with R <= 12; TAIL = R: every slot maskable) serve T down to half
+    // their slots; the others tolerate at most TAIL dead slots, all in the last lane
+    const bool short_series = TAIL == R && (G == 8 || (G == 16 && R <= 12));
+    return K <= KMAX && T <= G * R && (short_series ? 2 * T > G * R : G * R - T <= TAIL) && T >= 1;
 }
 
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,

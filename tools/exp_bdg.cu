@@ -128,6 +128,33 @@ int main(int argc, char **argv) {
         rung<20, 20, 16, 8, 4, 3, 0, 2>("G16 R20 SMH2 M3", b, 100);
         rung<20, 20, 16, 8, 4, 4, 1, 2>("G16 R20 SMH2 LEAN1 M4", b, 100);
         b.free_all();
+    } else if (set == 8) {      // round 2: short series with 28 taps -- four voxels per warp (G = 8) or two (G = 16)?
+        {
+            Bufs b; b.alloc(28416, 128, 0.72, 100);
+            rung<16, 28, 8, 16, 4, 2>("G8  R16 K28 M2 (T=128)", b, 100, true);
+            rung<8, 28, 16, 8, 4, 3>("G16 R8  K28 M3 (T=128)", b, 100);
+            rung<8, 28, 16, 8, 4, 4>("G16 R8  K28 M4 (T=128)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 96, 0.72, 100);
+            rung<13, 28, 8, 13, 4, 2>("G8  R13 K28 M2 (T=96)", b, 100, true);
+            rung<6, 28, 16, 6, 4, 4>("G16 R6  K28 M4 (T=96)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 190, 0.72, 100);
+            rung<24, 28, 8, 24, 4, 2>("G8  R24 K28 M2 (T=190)", b, 100, true);
+            rung<12, 28, 16, 12, 4, 3>("G16 R12 K28 M3 (T=190)", b, 100);
+            rung<12, 28, 16, 12, 4, 4>("G16 R12 K28 M4 (T=190)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 128, 1.0, 100);
+            rung<16, 20, 8, 16, 4, 3>("G8  R16 K20 M3 (T=128)", b, 100, true);
+            rung<8, 20, 16, 8, 4, 4>("G16 R8  K20 M4 (T=128)", b, 100);
+            b.free_all();
+        }
     } else if (set == 7) {      // round 2: four CTAs per SM (16 warps) without the shared-memory halo buffers
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 M3 (12 warps)", b, 100, true);
