@@ -139,6 +139,9 @@ def main():
                     % (t, real, real, R, K, G, tail, W, M))
             f.write('int fastg_wave_%s(int nb_iter) { return fast_bdg_wave<%s, %d, %d, %d, %d, %d, %d>(nb_iter); }\n'
                     % (t, real, R, K, G, tail, W, M))
+            f.write('int fastg_bd_es_%s(const BdArgs<%s> &a, cudaStream_t s) {\n'
+                    '    return fast_bdg_launch<%s, %d, %d, %d, %d, %d, %d, 0, 0, true>(a, s);\n}\n'
+                    % (t, real, real, R, K, G, tail, W, M))
             f.write('}  // namespace pb\n')
         grows.append((real, R, K, G, tail, t))
     crows = []
@@ -167,15 +170,16 @@ def main():
             for r2, R, K, NW, t in crows:
                 if r2 != real:
                     continue
-                f.write('        {%d, %d, %d, 0, fastc_ok_%s, fastc_bd_%s, fastc_wave_%s, nullptr},\n' % (R, K, 32 * NW, t, t, t))
+                f.write('        {%d, %d, %d, 0, fastc_ok_%s, fastc_bd_%s, fastc_wave_%s, nullptr, nullptr},\n' % (R, K, 32 * NW, t, t, t))
                 cnt += 1
-            f.write('        {0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr},\n')
+            f.write('        {0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr},\n')
             f.write('    };\n    *n = %d;\n    return table;\n}\n' % cnt)
         for real, R, K, G, tail, t in grows:
             f.write('bool fastg_ok_%s(int, int);\n' % t)
             f.write('int fastg_bd_%s(const BdArgs<%s> &, cudaStream_t);\n' % (t, real))
             f.write('int fastg_wave_%s(int);\n' % t)
             f.write('int fastg_deconv_%s(const DeconvArgs<%s> &, cudaStream_t);\n' % (t, real))
+            f.write('int fastg_bd_es_%s(const BdArgs<%s> &, cudaStream_t);\n' % (t, real))
         for real in ("float", "double"):
             f.write('template <> const FastGEntry<%s> *fastg_table<%s>(int *n) {\n' % (real, real))
             f.write('    static const FastGEntry<%s> table[] = {\n' % real)
@@ -183,7 +187,7 @@ def main():
             for r2, R, K, G, tail, t in grows:
                 if r2 != real:
                     continue
-                f.write('        {%d, %d, %d, %d, fastg_ok_%s, fastg_bd_%s, fastg_wave_%s, fastg_deconv_%s},\n' % (R, K, G, tail, t, t, t, t))
+                f.write('        {%d, %d, %d, %d, fastg_ok_%s, fastg_bd_%s, fastg_wave_%s, fastg_deconv_%s, fastg_bd_es_%s},\n' % (R, K, G, tail, t, t, t, t, t))
                 cnt += 1
             f.write('        {0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr},\n')
             f.write('    };\n    *n = %d;\n    return table;\n}\n' % cnt)

@@ -25,6 +25,7 @@ struct FastGEntry {
     int (*bd)(const BdArgs<real> &, cudaStream_t);
     int (*wave)(int nb_iter);
     int (*deconv)(const DeconvArgs<real> &, cudaStream_t);   // null for CTA variants
+    int (*bd_es)(const BdArgs<real> &, cudaStream_t);        // bd with early stopping (Q6 / Q7); null for CTA variants
 };
 
 template <typename real>
@@ -57,14 +58,14 @@ static const FastEntry<real> *pick(int T, int K) {
 // cheapest matching group / CTA variant: slots per voxel (lanes x samples per lane) x unrolled taps,
 // ties broken by the tail-select count
 template <typename real>
-static const FastGEntry<real> *pick_group(int T, int K) {
+static const FastGEntry<real> *pick_group(int T, int K, bool es = false) {
     const FastGEntry<real> *best = nullptr;
     long best_cost = 0;
     for (int which = 0; which < 2; ++which) {
         int n = 0;
         const FastGEntry<real> *t = which == 0 ? fastc_table<real>(&n) : fastg_table<real>(&n);
         for (int i = 0; i < n; ++i) {
-            if (!t[i].ok(T, K)) continue;
+            if (!t[i].ok(T, K) || (es && !t[i].bd_es)) continue;
             const long cost = (long)t[i].R * t[i].KMAX * t[i].G * 64 + t[i].TAIL;
             if (!best || cost < best_cost) {
                 best = &t[i];
@@ -79,10 +80,10 @@ template <typename real>
 static int bd_dispatch(const BdArgs<real> &a, cudaStream_t s) {
     // PB_DISABLE_GROUP=1: developer switch for A/B timing of the two register-tiled kernels
     static const bool no_group = getenv("PB_DISABLE_GROUP") != nullptr;
-    if (!a.early_stopping && !no_group) {
-        const FastGEntry<real> *ge = pick_group<real>(a.T, a.K);
+    if (!no_group) {
+        const FastGEntry<real> *ge = pick_group<real>(a.T, a.K, a.early_stopping != 0);
         if (ge) {
-            const int rc = ge->bd(a, s);
+            const int rc = a.early_stopping ? ge->bd_es(a, s) : ge->bd(a, s);
             if (rc != FAST_NO_MATCH) return rc;
         }
     }

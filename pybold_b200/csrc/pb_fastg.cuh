@@ -79,6 +79,18 @@ __device__ __forceinline__ float seg_scan_step_down(float inc, int d, int c) {
 #define PB_CORR_RB 7
 #endif
 
+// sqrt(x) for x >= 0 to double accuracy: float rsqrt estimate, one Newton step in double (6 FP64
+// instructions instead of the ~35 of the IEEE sequence; relative error ~1e-14)
+__device__ __forceinline__ double sqrt_refined(double x) {
+    if (!(x > 1.0e-300)) return x > 0.0 ? sqrt(x) : 0.0;
+    const float xf = (float)x;
+    if (!(xf > 1.0e-30f) || !(xf < 1.0e30f)) return sqrt(x);
+    const double r0 = (double)rsqrtf(xf);
+    const double r1 = r0 * fma(-0.5 * x, r0 * r0, 1.5);
+    const double r2 = r1 * fma(-0.5 * x, r1 * r1, 1.5);
+    return x * r2;
+}
+
 template <typename real, int G>
 struct Seg {
     static __device__ __forceinline__ real sum(real v) {
@@ -442,8 +454,14 @@ __host__ __device__ constexpr size_t fastg_warp_bytes() {
            (SMH == 2 ? (size_t)(2 * 32 + 1) * fastg_block_floats<R>() * sizeof(real) : 0);
 }
 
+// ES = true: the reference's `early_stopping=True` (non-default).  Q6 -- the inner loop of a voxel stops at
+// iteration j > 2 once ||w_j - u_j|| / (||w_j|| + 1e-10) < tol -- and Q7 -- the outer loop stops on the signed
+// change of the windowed means of J and runs one last pass -- are decided per GROUP; a group whose inner loop has
+// stopped keeps its iterate (predicated update) until its neighbour's has, a group whose voxel is finished
+// idles until its neighbour is (the double-precision phases stay in lock step for the warp), then the warp
+// takes the next task.  With ES = false none of this is compiled in.
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,
-          int SMH = 0>
+          int SMH = 0, bool ES = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_bdg_kernel(BdArgs<real> p) {
     constexpr int VPW = 32 / G;
@@ -554,15 +572,44 @@ fast_bdg_kernel(BdArgs<real> p) {
             rv[0] = real(1);
             gv[0] = (real)g0;
         }
+        bool live = on, stopped = false;                  // ES: per-group progress
+        int n_tr = 1;                                     // ES: trace entries written so far
+        double sumJ = 1.0;
         for (int idx = 0; idx <= p.nb_iter; ++idx) {
-            const bool last = idx == p.nb_iter;           // final deconvolution, :365-376
+            // final deconvolution, :365-376 (ES: also the pass after the outer stop fired, :350-362)
+            const bool last = ES ? (stopped || idx == p.nb_iter) : idx == p.nb_iter;
             const double Lc = frob_lipschitz_group<G>(sc, K, T, q);
             const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
-            for (int j = 0; j < p.nb_iter; ++j) {         // _loops_deconv, :259-276
-                real res[R], gr[R];
-                vx.forward(res);
-                vx.adjoint(res, gr);
-                vx.update(gr, step, th, beta[j]);
+            if constexpr (!ES) {
+                for (int j = 0; j < p.nb_iter; ++j) {     // _loops_deconv, :259-276
+                    real res[R], gr[R];
+                    vx.forward(res);
+                    vx.adjoint(res, gr);
+                    vx.update(gr, step, th, beta[j]);
+                }
+            } else {
+                bool frozen = !live;
+                for (int j = 0; j < p.nb_iter; ++j) {
+                    real res[R], gr[R];
+                    vx.forward(res);
+                    vx.adjoint(res, gr);
+                    const real ob = real(1) + beta[j];
+                    real pc = 0, pw = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const real u = fma(-step, gr[r], vx.w[r]);
+                        const real cl = fmin(fmax(u, -th), th);
+                        const real wn = fma(-ob, cl, u);
+                        pc = fma(cl, cl, pc);
+                        pw = fma(wn, wn, pw);
+                        vx.w[r] = frozen ? vx.w[r] : wn;
+                    }
+                    const double sc2 = (double)Seg<real, G>::sum(pc), sw2 = (double)Seg<real, G>::sum(pw);
+                    // Q6 (:267-273): ||w_j - u_j|| = (1 + beta_j) ||clamp(u_j)||
+                    const double num = (1.0 + (double)beta[j]) * sqrt_refined(sc2);
+                    if (j > 2 && num < p.tol * (sqrt_refined(sw2) + 1.0e-10)) frozen = true;
+                    if (__all_sync(PB_FULL, frozen)) break;
+                }
             }
             real z[R], hal[KMAX - 1], y[R];
 #pragma unroll
@@ -570,8 +617,9 @@ fast_bdg_kernel(BdArgs<real> p) {
             vx.scan_fwd(z);
             vx.halo_up(z, hal);
             vx.load_y(yv, T, y);
-            if (!last) {
+            if (ES ? __any_sync(PB_FULL, !last) : !last) {
                 // ---- theta step (:329-334): b = Z^T y, Rz = autocorrelation of z ----
+                // (ES: in lock step for the warp; a group in its last pass keeps its theta and taps)
                 real zm[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) zm[r] = z[r];
@@ -604,11 +652,12 @@ fast_bdg_kernel(BdArgs<real> p) {
                 gram_build_group<G>(sc, K, q);
 #ifdef PB_DEBUG_EVALS
                 int ne = 0;
-                theta = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, &ne);
+                const double th_new = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, &ne);
                 dbg_evals += ne;
 #else
-                theta = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, nullptr);
+                const double th_new = theta_solve_group<G>(theta, p.theta_lo, p.theta_hi, p.grid, sc, q, nullptr);
 #endif
+                theta = (ES && last) ? theta : th_new;
                 hrf_eval_group<G>(theta, p.grid, sc, q);
                 vx.load_taps(sc.hs, K);
             }
@@ -621,29 +670,65 @@ fast_bdg_kernel(BdArgs<real> p) {
             const double rr = (double)Seg<real, G>::sum(vx.partial_sumsq(xr));
             const double gg = (double)Seg<real, G>::sum(vx.partial_sumabs(vx.w));
             const double eps = last ? 0.0 : 1.0e-30;
-            if (writer) {
-                Jv[idx + 1] = (real)((rr + lam * gg) / j0 + eps);
-                rv[idx + 1] = (real)(rr / r0 + eps);
-                gv[idx + 1] = (real)gg;
-            }
-            if (last) {
+            if constexpr (!ES) {
+                if (writer) {
+                    Jv[idx + 1] = (real)((rr + lam * gg) / j0 + eps);
+                    rv[idx + 1] = (real)(rr / r0 + eps);
+                    gv[idx + 1] = (real)gg;
+                }
+                if (last) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) xr[r] += y[r];
-                vx.store(p.out_x + v * T, xr, T, on);
-                vx.store(p.out_z + v * T, z, T, on);
-                vx.store(p.out_dz + v * T, vx.w, T, on);
+                    for (int r = 0; r < R; ++r) xr[r] += y[r];
+                    vx.store(p.out_x + v * T, xr, T, on);
+                    vx.store(p.out_z + v * T, z, T, on);
+                    vx.store(p.out_dz + v * T, vx.w, T, on);
+                }
+            } else {
+                const double Jn = (rr + lam * gg) / j0 + eps;
+                if (writer && live) {
+                    Jv[n_tr] = (real)Jn;
+                    rv[n_tr] = (real)(rr / r0 + eps);
+                    gv[n_tr] = (real)gg;
+                }
+                if (live) {
+                    sumJ += (double)(real)Jn;
+                    ++n_tr;
+                }
+                if (last && live) {                       // this voxel is done: everything it returns, now
+#pragma unroll
+                    for (int r = 0; r < R; ++r) xr[r] += y[r];
+                    vx.store(p.out_x + v * T, xr, T, true);
+                    vx.store(p.out_z + v * T, z, T, true);
+                    vx.store(p.out_dz + v * T, vx.w, T, true);
+                    for (int a = q; a < K; a += G) p.out_h[v * K + a] = (real)sc.hs[a];
+                    if (q == 0) {
+                        p.out_theta[v] = (real)theta;
+                        p.out_ntrace[v] = n_tr;
+                    }
+                    live = false;
+                }
+                __syncwarp();
+                if (idx > p.wind) {                       // Q7 (:350-362); warp-uniform condition
+                    int stop = 0;
+                    if (live && q == 0) stop = bd_outer_stop(Jv, n_tr, sumJ, p.wind / 2, p.tol) ? 1 : 0;
+                    stop = __shfl_sync(PB_FULL, stop, 0, G);
+                    if (live) stopped = stop != 0;
+                }
+                if (!__any_sync(PB_FULL, live)) break;
             }
             __syncwarp();
         }
-        if (on)
-            for (int a = q; a < K; a += G) p.out_h[v * K + a] = (real)sc.hs[a];
-        if (writer) {
-            p.out_theta[v] = (real)theta;
+        if constexpr (!ES) {
+            if (on)
+                for (int a = q; a < K; a += G) p.out_h[v * K + a] = (real)sc.hs[a];
+            if (writer) {
+                p.out_theta[v] = (real)theta;
 #ifdef PB_DEBUG_EVALS
-            p.out_ntrace[v] = dbg_evals;
+                p.out_ntrace[v] = dbg_evals;
 #else
-            p.out_ntrace[v] = ntr;
+                p.out_ntrace[v] = ntr;
 #endif
+            }
         }
         __syncwarp();
     }
@@ -760,18 +845,6 @@ fast_deconvg_kernel(DeconvArgs<real> p) {
 // Ring of the past u's (Q5 window): [slot][lane][RP] in shared memory, every lane reads and writes its
 // own 16-byte aligned block with vector accesses (RP / 4 odd: conflict free).
 // ------------------------------------------------------------------------------------------------
-// sqrt(x) for x >= 0 to double accuracy: float rsqrt estimate, one Newton step in double (6 FP64
-// instructions instead of the ~35 of the IEEE sequence; relative error ~1e-14)
-__device__ __forceinline__ double sqrt_refined(double x) {
-    if (!(x > 1.0e-300)) return x > 0.0 ? sqrt(x) : 0.0;
-    const float xf = (float)x;
-    if (!(xf > 1.0e-30f) || !(xf < 1.0e30f)) return sqrt(x);
-    const double r0 = (double)rsqrtf(xf);
-    const double r1 = r0 * fma(-0.5 * x, r0 * r0, 1.5);
-    const double r2 = r1 * fma(-0.5 * x, r1 * r1, 1.5);
-    return x * r2;
-}
-
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 fast_deconvg_es_kernel(DeconvArgs<real> p, int ring_rows) {
@@ -1005,12 +1078,12 @@ bool fastg_shape_ok(int T, int K) {
 }
 
 template <typename real, int R, int KMAX, int G, int TAIL, int WARPS, int MINB, int LEAN = 0,
-          int SMH = 0>
+          int SMH = 0, bool ES = false>
 int fast_bdg_launch(const BdArgs<real> &a, cudaStream_t stream) {
     constexpr int VPW = 32 / G;
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
     const size_t smem = beta_bytes + (size_t)WARPS * fastg_warp_bytes<real, R, KMAX, G, LEAN, SMH>();
-    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH>;
+    auto kern = fast_bdg_kernel<real, R, KMAX, G, TAIL, WARPS, MINB, LEAN, SMH, ES>;
     int dev = 0, sms = 0, max_smem = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
