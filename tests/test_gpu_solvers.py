@@ -220,6 +220,36 @@ def test_bd_fp32_vs_fp64():
     assert rel(got[3], ref[3]) < 1e-4          # h
 
 
+@pytest.mark.parametrize("T,t_r", [(300, 1.0), (240, 0.75), (150, 1.0)])
+def test_bd_early_stopping_group_kernel(T, t_r):
+    """bd(early_stopping=True) on the group layout (round 2): the inner Q6 stop fires at a different iteration
+    for every voxel of a warp and the outer Q7 stop ends the run early.  FP64 against the oracle running the
+    same exact theta step; a voxel solved in a batch == the same voxel solved alone (bit exact); FP32 1e-4."""
+    import pybold_b200 as pb
+    from pybold_b200 import _lib
+    V = 5
+    y = gen_voxels(V, T, t_r, 20.0, seed0=2500 + T)
+    y *= np.linspace(0.5, 2.0, V)[:, None]
+    kw = dict(lbda=1.7, theta_0=2.0, hrf_dur=20.0, nb_iter=30, early_stopping=True, wind=4, tol=2.0e-3)
+    x, z, dz, h, d = pb.bd(y, t_r, **kw)
+    n_tr = d["n_trace"]
+    assert np.all(n_tr < 32) and np.all(n_tr >= 6)            # Q7 ended every run early
+    for v in range(V):
+        xo, zo, wo, ho, do = orc.bd(y[v], t_r, theta_solver="exact", **kw)
+        assert len(do["J"]) == n_tr[v], v
+        assert rel(z[v], zo) < 1e-7 and rel(dz[v], wo) < 1e-7 and rel(h[v], ho) < 1e-7, v
+        assert rel(d["J"][v, :n_tr[v]], do["J"]) < 1e-8, v
+        x1, z1, dz1, h1, d1 = pb.bd(y[v], t_r, **kw)
+        assert np.array_equal(z1, z[v]) and np.array_equal(d1["J"], d["J"][v, :n_tr[v]]), v
+    K = h.shape[1]
+    if _lib.lib.pb_solver_variant(T, K, 0) // 1000000 <= 16:
+        x32, z32, dz32, h32, d32 = pb.bd(y.astype(np.float32), t_r, **kw)
+        assert np.array_equal(d32["n_trace"], n_tr)
+        assert rel(z32, z) < 1e-4 and rel(h32, h) < 1e-4
+        for v in range(V):
+            assert rel(d32["J"][v, :n_tr[v]], d["J"][v, :n_tr[v]]) < 1e-4
+
+
 def test_bd_per_voxel_parameters_and_tensor_io():
     import pybold_b200 as pb
     V, T = 5, 300
