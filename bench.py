@@ -492,15 +492,19 @@ def main():
         res = step_e2e()     # two untimed calls: the pinned result blocks of two consecutive calls
         res = step_e2e()     # (the caller still holds the previous result) are then both cached
         barrier()
+        e2e_samples = []
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            res = step_e2e()
+            t_s = time.perf_counter()
+            res = step_e2e()                 # returns host arrays: the call ends when they are complete
+            e2e_samples.append((time.perf_counter() - t_s) * 1e3)
         barrier()
         (e2e_s,) = max_over_ranks([(time.perf_counter() - t0) / args.steps])
         d2h = sum(int(a.numel()) * a.element_size() for a in res[:4]) + \
             sum(int(res[4][k].numel()) * res[4][k].element_size() for k in ("J", "r", "g", "theta", "n_trace"))
         e2e = {"value": V_total / e2e_s, "unit": "voxels/s",
-               "h2d_bytes_per_step": int(y_host.numel()) * 4, "d2h_bytes_per_step": int(d2h)}
+               "h2d_bytes_per_step": int(y_host.numel()) * 4, "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s * 1e3, "ms_per_step_rank0": [round(v, 2) for v in e2e_samples]}
         del res
 
     # ---- extra: the other BASELINE.json configurations, device-timed --------------------------------
