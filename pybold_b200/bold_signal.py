@@ -242,18 +242,13 @@ def _bd_streamed(yh, dtype, t_r, lbda, theta_0, z_0, hrf_dur, bounds, nb_iter, e
     dev = torch.device("cuda", torch.cuda.current_device())
     K = hrf_len(t_r, hrf_dur)
     ntr = nb_iter + 2
-    # Chunking: the kernels of consecutive chunks run on two streams and pull their tasks from work queues, so
-    # the tail of one chunk's solve overlaps the head of the next and chunks need not be whole waves of the
-    # grid; EQUAL chunks avoid a small remainder chunk (it used to cost two partial waves).  PB_NO_QUEUE
-    # (static scheduling, developer switch) keeps the wave-aligned chunks of round 1.
-    import os
+    # Chunks of whole waves of the persistent grid (no partially filled last wave inside a chunk).  Equal,
+    # non-wave-aligned chunks were measured in round 2 and rejected: the kernels of consecutive chunks (two
+    # streams) do not overlap at their tails, 4 x 25 000 voxels took 631 ms against 591-599 for 3 x 31 968 + 4 096.
     wave = _lib.lib.pb_bd_wave_voxels(T, K, int(dtype == torch.float64), int(nb_iter))
-    if os.environ.get("PB_NO_QUEUE") and wave > 0:
-        chunk = max(wave, (_STREAM_TARGET_CHUNK // wave) * wave)
-    else:
-        n_chunks = max(1, int(round(V / float(_STREAM_TARGET_CHUNK))))
-        chunk = -(-V // n_chunks)
-        chunk = -(-chunk // 16) * 16
+    chunk = _STREAM_TARGET_CHUNK
+    if wave > 0:
+        chunk = max(wave, (chunk // wave) * wave)
     chunk = min(chunk, V)
     shapes = {"x": (chunk, T), "z": (chunk, T), "diff_z": (chunk, T), "h": (chunk, K),
               "theta": (chunk,), "J": (chunk, ntr), "r": (chunk, ntr), "g": (chunk, ntr),
