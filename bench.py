@@ -236,7 +236,7 @@ def run_reference(args):
         "unmodified pybold.bold_signal.bd from baseline/_ref" if kind == "reference"
         else "oracle port of pybold.bold_signal.bd (baseline/_ref absent)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value,
+        "impl": "reference", "metric": METRIC.replace("300", str(w["n_scans"])), "value": value,
         "unit": "voxels/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -636,8 +636,10 @@ def main():
             torch.cuda.empty_cache()
 
     if rank == 0:
-        roofline = fp32_roofline("bd", V, T, K, n, kern_ms, "fast_bdg_kernel (variant %d)"
-                                 % _lib.lib.pb_solver_variant(T, K, 0))
+        vid = _lib.lib.pb_solver_variant(T, K, 0)
+        roofline = fp32_roofline("bd", V, T, K, n, kern_ms, "%s (variant %d = lanes per voxel x 1e6 + samples per "
+                                 "lane x 1e3 + unrolled taps)" % ("fast_bdg_kernel" if vid // 1000000 <= 16 else
+                                                                   "fast_bdc_kernel" if vid else "generic_bd_kernel", vid))
         roofline["kernel_ms_per_step"] = solver_ms
         tr_bytes, tr_src = ncu_traffic(cfg["workload"])
         roofline["traffic"] = tr_bytes
@@ -658,7 +660,7 @@ def main():
                                                        "unmodified pybold.bold_signal.bd (baseline/_ref)"
                                                        if kind == "reference" else "oracle port")}
         line = {
-            "metric": METRIC, "value": value, "unit": "voxels/s",
+            "metric": METRIC.replace("300", str(T)), "value": value, "unit": "voxels/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
