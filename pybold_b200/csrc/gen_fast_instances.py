@@ -84,6 +84,11 @@ CVARIANTS = [
     # R = 12 and R = 20 variants -- T in (384, 512], (768, 1024], (1152, 1536], (1536, 2048], (3072, 4096]
     ("float", 16, K, NW, M) for K in (20, 28) for (NW, M) in ((1, 12), (2, 6), (3, 4), (4, 3), (8, 2))
 ] + [
+    # six warps per voxel: two CTAs of 168-register threads per SM (eight warps leave room for one, or spill
+    # at 128 registers): 2560 < T <= 4096
+    # (R = 24 was measured slower than eight warps of R = 16 at T = 4096 and is not built)
+    ("float", R, K, 6, 2) for K in (20, 28, 40) for R in (16, 20)
+] + [
     # round 2: short-TR acquisitions, 28 < K <= 40 (TR >= 0.5 s) and K <= 64 (TR >= 0.32 s), every T <= 4096.
     # More taps, more registers (taps, halo and tile live in registers): launch bounds leave ~170 (K = 40)
     # and ~250 (K = 64) registers per thread

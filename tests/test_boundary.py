@@ -113,7 +113,7 @@ def test_dispatch_covers_every_series_length():
     assert _lib.lib.pb_solver_variant(600, 20, 0) == 32020020
     assert _lib.lib.pb_solver_variant(150, 20, 0) // 1000000 == 8    # four voxels per warp
     assert _lib.lib.pb_solver_variant(2000, 28, 0) == 128016028     # four warps, R = 16 (skewed layout)
-    assert _lib.lib.pb_solver_variant(3000, 20, 0) == 256016020      # eight warps per voxel
+    assert _lib.lib.pb_solver_variant(3000, 20, 0) == 192016020      # six warps per voxel
     # round 2: every K <= 64 (TR down to 0.32 s at hrf_dur = 20 s) and T <= 4096 has a register-tiled variant
     for K in (29, 40, 41, 64):
         for T in list(range(1, 200, 3)) + list(range(200, 4097, 37)) + [4096]:
@@ -123,7 +123,7 @@ def test_dispatch_covers_every_series_length():
             assert lanes * R >= T and kmax >= K, (T, K, vid)
     for K in (20, 28):
         for T in range(2561, 4097, 41):
-            assert _lib.lib.pb_solver_variant(T, K, 0) // 1000000 == 256, (T, K)
+            assert _lib.lib.pb_solver_variant(T, K, 0) // 1000000 in (192, 256), (T, K)
     assert _lib.lib.pb_solver_variant(300, 40, 0) == 32012040
     assert _lib.lib.pb_solver_variant(300, 65, 0) == 0               # beyond PB_MAX_K: generic kernel
 

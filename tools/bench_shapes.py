@@ -20,10 +20,14 @@ sms = torch.cuda.get_device_properties(0).multi_processor_count
 nominal = sms * 128 * 2 * 1.965e9 / 1e12
 Ts = [64, 96, 100, 128, 150, 190, 200, 240, 256, 300, 320, 350, 384, 405, 450, 500, 512, 600, 650, 700, 768, 800,
       900, 1000, 1050, 1150, 1200, 1280, 1500, 2000, 2400, 2560, 3000, 4096]
+import os
+if os.environ.get("PB_SHAPES_TS"):          # e.g. PB_SHAPES_TS=2600,3000,4096 PB_SHAPES_TR=1.0,0.72
+    Ts = [int(v) for v in os.environ["PB_SHAPES_TS"].split(",")]
+TRs = [float(v) for v in os.environ.get("PB_SHAPES_TR", "1.0,0.75,0.72,0.5,0.32").split(",")]
 print("bd, FP32, nb_iter = %d, %d waves of the grid per shape; fraction of the nominal FP32 peak (%.1f Tflop/s)" % (n, waves, nominal))
 print("%5s %3s %10s %8s %9s %11s %8s %6s" % ("T", "K", "variant", "voxels", "ms", "voxels/s", "Tflop/s", "frac"))
 worst = {}
-for t_r in (1.0, 0.75, 0.72, 0.5, 0.32):
+for t_r in TRs:
     K = hrf_len(t_r, 20.0)
     for T in Ts:
         wave = _lib.lib.pb_bd_wave_voxels(T, K, 0, n)
