@@ -93,10 +93,17 @@ CVARIANTS = [
     # More taps, more registers (taps, halo and tile live in registers): launch bounds leave ~170 (K = 40)
     # and ~250 (K = 64) registers per thread
     ("float", R, 40, NW, M)
-    for (R, NW, M) in ((4, 1, 12), (8, 1, 12), (12, 1, 12), (20, 1, 12), (20, 2, 6), (20, 4, 3), (20, 8, 1))
+    for (R, NW, M) in ((4, 1, 12), (8, 1, 12), (12, 1, 12), (20, 1, 12), (20, 2, 6), (20, 4, 3), (20, 8, 1),
+                       # the gaps between them (as for K <= 28): T in (384, 512], (640, 768], (768, 1024],
+                       # (1280, 1536], (1536, 1920], (1920, 2048]
+                       (16, 1, 12), (12, 2, 6), (16, 2, 6), (16, 3, 4), (20, 3, 4), (16, 4, 3))
 ] + [
     ("float", R, 64, NW, M)
-    for (R, NW, M) in ((4, 1, 8), (8, 1, 8), (12, 1, 8), (20, 1, 8), (20, 2, 4), (20, 4, 2), (20, 8, 1))
+    for (R, NW, M) in ((4, 1, 8), (8, 1, 8), (12, 1, 8), (20, 1, 8), (20, 2, 4), (20, 4, 2), (20, 8, 1),
+                       (16, 1, 8), (12, 2, 4), (16, 2, 4), (20, 3, 2),
+                       # the 64-tap scratch (double Gram matrix) leaves room for four CTAs per SM: with one
+                       # warp per voxel that is four warps per SM, with two it is the eight the registers allow
+                       (4, 2, 4), (8, 2, 4))
 ]
 
 

@@ -338,7 +338,11 @@ def test_bd_long_series_four_warp_variant_vs_generic_fp64():
 @pytest.mark.parametrize("T,t_r,n_it", [(200, 0.5, 12), (600, 0.5, 8), (90, 0.5, 10), (40, 0.5, 10), (1000, 0.5, 6),
                                         (2000, 0.5, 4), (3000, 0.5, 3), (300, 0.32, 10), (1200, 0.32, 5),
                                         (4096, 0.32, 3), (3000, 1.0, 3), (4096, 0.72, 3), (2600, 1.0, 4),
-                                        (3500, 1.0, 3), (3600, 0.5, 3), (3900, 0.72, 3)])
+                                        (3500, 1.0, 3), (3600, 0.5, 3), (3900, 0.72, 3),
+                                        # gap-filling variants of the 40- and 64-tap families
+                                        (450, 0.5, 8), (700, 0.5, 8), (900, 0.5, 6), (1500, 0.5, 5), (1800, 0.5, 4),
+                                        (150, 0.32, 10), (200, 0.32, 10), (450, 0.32, 8), (700, 0.32, 8),
+                                        (900, 0.32, 6), (1500, 0.32, 5)])
 def test_bd_short_tr_and_long_series_variants(T, t_r, n_it):
     """Round 2 variants: 28 < K <= 64 taps (TR 0.5 s -> K = 40, TR 0.32 s -> K = 63) and 2560 < T <= 4096
     (six or eight warps per voxel) run register-tiled in FP32; the FP64 build of these shapes is the generic
