@@ -40,12 +40,43 @@ def to_device(x, dtype, device=None):
     return torch.from_numpy(arr).to(device=device, dtype=dtype).contiguous()
 
 
+_scalar_cache = {}
+
+
+def _device_scalar(v, dtype, device):
+    """One-element device tensor holding ``v``; cached (read-only by convention: kernels only load it), so a
+    scalar lbda / theta_0 costs no upload, and no host wait on the stream, after its first use."""
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (v, dtype, device)
+    t = _scalar_cache.get(key)
+    if t is None:
+        if len(_scalar_cache) >= 256:
+            _scalar_cache.clear()
+        t = torch.full((1,), v, dtype=dtype, device=device)
+        if device.type == "cuda":
+            torch.cuda.current_stream(device).synchronize()      # complete before another stream may read it
+        _scalar_cache[key] = t
+    return t
+
+
 def per_voxel(value, V, dtype, device, name):
     """Scalar or length-V parameter -> (tensor, element stride) as the C ABI wants it."""
     if isinstance(value, torch.Tensor):
         t = value.to(device=device, dtype=dtype).reshape(-1).contiguous()
     else:
-        t = torch.as_tensor(np.asarray(value, dtype=np.float64).reshape(-1)).to(device=device, dtype=dtype)
+        arr = np.asarray(value, dtype=np.float64).reshape(-1)
+        if arr.size == 1:
+            return _device_scalar(float(arr[0]), dtype, torch.device(device)), 0
+        # through a pinned block (PyTorch caches them) and an asynchronous copy: a pageable upload makes the
+        # host wait on the launch stream, and that wait was measured to stall for tens of milliseconds now and
+        # then (tools/debug_e2e.py) -- with the device idle, since the solver launch follows it
+        stage = torch.empty(arr.size, dtype=dtype, pin_memory=True) if torch.device(device).type == "cuda" else None
+        if stage is None:
+            t = torch.as_tensor(arr).to(device=device, dtype=dtype)
+        else:
+            stage.copy_(torch.from_numpy(arr))
+            t = stage.to(device=device, non_blocking=True)
     if t.numel() == 1:
         return t, 0
     if t.numel() != V:
