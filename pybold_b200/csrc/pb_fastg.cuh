@@ -156,6 +156,9 @@ struct Seg<float, G> {
 // values there (ceil(R / 4) STS.128) and reads the blocks of the lanes before / after it (LDS.128).  The
 // lanes at the ends of a group read a block of zeros instead, picked once per kernel through a pointer:
 // no boundary selects.  K = 20, R = 19: 5 + 5 instead of 19 SHFL + 19 FSEL per exchange.
+#ifndef PB_HALO_PRED
+#define PB_HALO_PRED 0
+#endif
 #ifdef PB_LEAN_KEEP_TAPS
 constexpr bool kLeanTaps = false;   // experiment: LEAN moves only dy to shared memory
 #else
@@ -184,10 +187,19 @@ struct GroupVoxel {
     const real *h_s;               // LEAN: this group's KMAX taps, 16-byte aligned
     int nvalid;                    // samples (< T) this lane holds
     int q;                         // lane within the group
+    // PRED (PB_HALO_PRED): no select after the halo shuffles; the FFMA consuming a halo value of hop d is
+    // predicated on the existence of lane q -+ d (pb_tile.cuh: fma_if)
+    static constexpr bool PRED = PB_HALO_PRED != 0 && SMH == 0 && !LT && sizeof(real) == 4;
+    unsigned ok_up[DUP], ok_dn[DUP];
 
     __device__ __forceinline__ void init(int lane, int T) {
         q = lane & (G - 1);
         nvalid = max(0, min(R, T - q * R));
+#pragma unroll
+        for (int d = 1; d <= DUP; ++d) {
+            ok_up[d - 1] = q >= d ? 1u : 0u;
+            ok_dn[d - 1] = q + d < G ? 1u : 0u;
+        }
     }
     // SMH = 2: store the R values as ceil(R / 4) vectors (the pad of the last one is never used)
     __device__ __forceinline__ void put_block(real *dst, const real (&a)[R]) const {
@@ -209,6 +221,8 @@ struct GroupVoxel {
         }
     }
     // halo[m-1] = a at voxel index (q R - m), zero before the series starts
+    // (RAW: for the inner loop of a PRED build -- values of non-existent lanes are left in, see fma_if)
+    template <bool RAW = false>
     __device__ __forceinline__ void halo_up(const real (&a)[R], real (&halo)[KMAX - 1]) const {
         if constexpr (SMH == 2) {
             put_block(myA, a);
@@ -250,10 +264,11 @@ struct GroupVoxel {
             const int d = (m + R - 1) / R;
             const int rr = d * R - m;
             const real t = __shfl_up_sync(PB_FULL, a[rr], d, G);
-            halo[m - 1] = q >= d ? t : real(0);
+            halo[m - 1] = (RAW && PRED) ? t : (q >= d ? t : real(0));
         }
     }
     // halo[k] = a at voxel index (q R + R + k), zero past the last lane of the group
+    template <bool RAW = false>
     __device__ __forceinline__ void halo_down(const real (&a)[R], real (&halo)[KMAX - 1]) const {
         if constexpr (SMH == 2) {
             put_block(myB, a);
@@ -293,7 +308,7 @@ struct GroupVoxel {
             const int d = (R + k) / R;
             const int rr = (R + k) - d * R;
             const real t = __shfl_down_sync(PB_FULL, a[rr], d, G);
-            halo[k] = q + d < G ? t : real(0);
+            halo[k] = (RAW && PRED) ? t : (q + d < G ? t : real(0));
         }
     }
     struct alignas(4 * sizeof(real)) Tap4 { real t[4]; };
@@ -317,7 +332,7 @@ struct GroupVoxel {
                 }
             }
         } else {
-            tile_conv<real, R, KMAX, KMAX - 1, JS, PB_CONV_JDESC, PB_CONV_RDESC, PB_CONV_RB, PB_CONV_DS>(h, a, halo, acc);
+            tile_conv<real, R, KMAX, KMAX - 1, JS, PB_CONV_JDESC, PB_CONV_RDESC, PB_CONV_RB, PB_CONV_DS, PRED>(h, a, halo, acc, ok_up);
         }
     }
     template <int JS>
@@ -340,7 +355,7 @@ struct GroupVoxel {
                 }
             }
         } else {
-            tile_corr<real, R, KMAX, KMAX - 1, JS, PB_CORR_JDESC, PB_CORR_RDESC, PB_CORR_RB, PB_CORR_DS>(h, a, halo, acc);
+            tile_corr<real, R, KMAX, KMAX - 1, JS, PB_CORR_JDESC, PB_CORR_RDESC, PB_CORR_RB, PB_CORR_DS, PRED>(h, a, halo, acc, ok_dn);
         }
     }
     __device__ __forceinline__ void scan_fwd(real (&a)[R]) const {
@@ -358,7 +373,7 @@ struct GroupVoxel {
     // res <- A w - y
     __device__ __forceinline__ void forward(real (&res)[R]) const {
         real halo[KMAX - 1];
-        halo_up(w, halo);
+        halo_up<true>(w, halo);
 #pragma unroll
         for (int r = 0; r < R; ++r) res[r] = LEAN ? -dy_s[r * 32] : -dy[LEAN ? 0 : r];
         conv_acc<J0>(w, halo, res);
@@ -372,7 +387,7 @@ struct GroupVoxel {
     // g <- A^T res
     __device__ __forceinline__ void adjoint(const real (&res)[R], real (&g)[R]) const {
         real halo[KMAX - 1];
-        halo_down(res, halo);
+        halo_down<true>(res, halo);
 #pragma unroll
         for (int r = 0; r < R; ++r) g[r] = real(0);
         corr_acc<J0>(res, halo, g);

@@ -12,6 +12,18 @@
 
 namespace pb {
 
+// Predicated FMA: acc += h * v only where ok != 0 (one predicate per halo hop, constant over the kernel).
+// The lanes at the ends of a voxel's lane group have no neighbour to take a halo from; instead of zeroing
+// every halo value with a select after the shuffle, the FFMA that would consume it is predicated off.
+__device__ __forceinline__ float fma_if(float h, float v, float acc, unsigned ok) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p fma.rn.f32 %0, %1, %2, %0;\n\t}"
+        : "+f"(acc) : "f"(h), "f"(v), "r"(ok));
+    return acc;
+}
+__device__ __forceinline__ double fma_if(double h, double v, double acc, unsigned ok) {
+    return ok ? fma(h, v, acc) : acc;
+}
+
 struct TileOrder {
     int jdesc;   // taps from K-1 down to JS instead of JS .. K-1
     int rdesc;   // samples from R-1 down to 0
@@ -20,9 +32,18 @@ struct TileOrder {
 };
 
 // causal: acc[r] += h[j] * x[r - j],  x[i] = a[i] (i >= 0) or halo[-i - 1]
-template <typename real, int R, int KMAX, int NHALO, int JS, int JDESC, int RDESC, int RB_, int DS>
+// PRED: halo values are raw (not zeroed at the ends of the lane group); ok[d - 1] != 0 where the lane d
+// positions away exists
+template <typename real, int R, int KMAX, int NHALO, int JS, int JDESC, int RDESC, int RB_, int DS, bool PRED = false>
 __device__ __forceinline__ void tile_conv(const real (&h)[KMAX], const real (&a)[R],
-                                          const real (&halo)[NHALO], real (&acc)[R]) {
+                                          const real (&halo)[NHALO], real (&acc)[R],
+                                          const unsigned *ok = nullptr) {
+    // PRED: the first FFMA of an accumulator must not be a predicated one (its initial value would need a
+    // select): the tap-JS terms on own samples go first
+    if constexpr (PRED) {
+#pragma unroll
+        for (int r = JS; r < R; ++r) acc[r] = fma(h[JS], a[r - JS], acc[r]);
+    }
     if constexpr (DS != 0) {
 #pragma unroll
         for (int ii = -(KMAX - 1); ii < R; ++ii) {
@@ -32,7 +53,13 @@ __device__ __forceinline__ void tile_conv(const real (&h)[KMAX], const real (&a)
             for (int jj = JS; jj < KMAX; ++jj) {
                 const int j = JDESC ? KMAX - 1 + JS - jj : jj;
                 const int r = i + j;
-                if (r >= 0 && r < R) acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
+                if (PRED && j == JS && i >= 0) continue;
+                if (r >= 0 && r < R) {
+                    if (PRED && i < 0)
+                        acc[r >= 0 && r < R ? r : 0] = fma_if(h[j], val, acc[r >= 0 && r < R ? r : 0], ok[i < 0 ? (-i + R - 1) / R - 1 : 0]);
+                    else
+                        acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
+                }
             }
         }
     } else {
@@ -47,7 +74,9 @@ __device__ __forceinline__ void tile_conv(const real (&h)[KMAX], const real (&a)
                     const int r = RDESC ? R - 1 - rr : rr;
                     const int idx = r - j;
                     const real val = idx >= 0 ? a[idx >= 0 ? idx : 0] : halo[idx >= 0 ? 0 : -idx - 1];
-                    acc[r] = fma(h[j], val, acc[r]);
+                    if (PRED && j == JS && idx >= 0) continue;
+                    if (PRED && idx < 0) acc[r] = fma_if(h[j], val, acc[r], ok[idx < 0 ? (-idx + R - 1) / R - 1 : 0]);
+                    else acc[r] = fma(h[j], val, acc[r]);
                 }
             }
         }
@@ -55,9 +84,14 @@ __device__ __forceinline__ void tile_conv(const real (&h)[KMAX], const real (&a)
 }
 
 // anti-causal: acc[r] += h[j] * x[r + j],  x[i] = a[i] (i < R) or halo[i - R]
-template <typename real, int R, int KMAX, int NHALO, int JS, int JDESC, int RDESC, int RB_, int DS>
+template <typename real, int R, int KMAX, int NHALO, int JS, int JDESC, int RDESC, int RB_, int DS, bool PRED = false>
 __device__ __forceinline__ void tile_corr(const real (&h)[KMAX], const real (&a)[R],
-                                          const real (&halo)[NHALO], real (&acc)[R]) {
+                                          const real (&halo)[NHALO], real (&acc)[R],
+                                          const unsigned *ok = nullptr) {
+    if constexpr (PRED) {
+#pragma unroll
+        for (int r = 0; r + JS < R; ++r) acc[r] = fma(h[JS], a[r + JS], acc[r]);
+    }
     if constexpr (DS != 0) {
 #pragma unroll
         for (int ii = 0; ii < R + KMAX - 1; ++ii) {
@@ -67,7 +101,13 @@ __device__ __forceinline__ void tile_corr(const real (&h)[KMAX], const real (&a)
             for (int jj = JS; jj < KMAX; ++jj) {
                 const int j = JDESC ? KMAX - 1 + JS - jj : jj;
                 const int r = i - j;
-                if (r >= 0 && r < R) acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
+                if (PRED && j == JS && i < R) continue;
+                if (r >= 0 && r < R) {
+                    if (PRED && i >= R)
+                        acc[r >= 0 && r < R ? r : 0] = fma_if(h[j], val, acc[r >= 0 && r < R ? r : 0], ok[i >= R ? i / R - 1 : 0]);
+                    else
+                        acc[r >= 0 && r < R ? r : 0] = fma(h[j], val, acc[r >= 0 && r < R ? r : 0]);
+                }
             }
         }
     } else {
@@ -82,7 +122,9 @@ __device__ __forceinline__ void tile_corr(const real (&h)[KMAX], const real (&a)
                     const int r = RDESC ? R - 1 - rr : rr;
                     const int idx = r + j;
                     const real val = idx < R ? a[idx < R ? idx : 0] : halo[idx < R ? 0 : idx - R];
-                    acc[r] = fma(h[j], val, acc[r]);
+                    if (PRED && j == JS && idx < R) continue;
+                    if (PRED && idx >= R) acc[r] = fma_if(h[j], val, acc[r], ok[idx >= R ? idx / R - 1 : 0]);
+                    else acc[r] = fma(h[j], val, acc[r]);
                 }
             }
         }

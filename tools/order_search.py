@@ -45,7 +45,7 @@ def main():
     def run(i):
         c = cands[i]
         out = os.path.join(tmp, "c%d.cubin" % i)
-        flags = ["-D%s%s=%d" % (pre, k, v) for k, v in c.items()]
+        flags = ["-D%s%s=%d" % (pre, k, v) for k, v in c.items()] + os.environ.get("PB_EXTRA_FLAGS", "").split()
         subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
                         "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "pybold_b200", "csrc")] + flags +
                        ["-cubin", "-o", out, src], check=True, capture_output=True)
