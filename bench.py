@@ -245,11 +245,31 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on rank 0's stdout.  Libraries write there too (NCCL prints its version
+    banner on stdout when NCCL_DEBUG is set in the environment): keep a private handle on the real stdout for
+    the result line and point file descriptor 1 at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -675,7 +695,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

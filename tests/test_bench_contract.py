@@ -56,3 +56,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["config"] == want
     # the reference arm must not have loaded the product library
     assert "pybold_b200" not in out.stderr
+
+
+def test_stdout_carries_only_the_result_line():
+    """Libraries write to file descriptor 1 (NCCL's version banner with NCCL_DEBUG set): the bench keeps a
+    private handle for its JSON line and sends everything else to stderr."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'NCCL version x.y\\n'); print('noise'); bench.emit({'a': 1})" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert "NCCL version" in r.stderr and "noise" in r.stderr
