@@ -35,3 +35,11 @@ for name, fn in [("integ op (cumsum)", lambda: D.op(x)), ("integ adj", lambda: D
                  ("torch copy (reference)", lambda: x.clone())]:
     ms = timed(fn)
     print("%-32s %8.3f ms  %7.1f GB/s  %.2f of measured HBM copy (%.0f GB/s)" % (name, ms, byt / ms / 1e6, byt / ms / 1e6 / peak, peak))
+
+# tap-count sweep of the convolution: at full HBM rate a K-tap row kernel must also sustain K FFMA per 8 bytes
+# (K = 28: 46 Tflop/s, 0.62 of the nominal FP32 pipe) -- fewer taps show what the memory path alone delivers
+for Kx in (4, 8, 12, 20, 28):
+    kx = torch.rand(Kx, device="cuda")
+    ms = timed(lambda: simple_convolve(kx, x))
+    print("%-32s %8.3f ms  %7.1f GB/s  %.2f of measured HBM copy  (%.1f Tflop/s of FFMA)"
+          % ("conv op (K=%d)" % Kx, ms, byt / ms / 1e6, byt / ms / 1e6 / peak, 2.0 * V * T * Kx / ms / 1e9))
