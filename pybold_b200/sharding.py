@@ -204,11 +204,31 @@ class PeerGather:
             dist.barrier(group=self.group)
 
 
-def bd_sharded(y_full_or_local, n_voxels, solve, gather=True, group=None):
+_peer_gatherers = {}
+
+
+def _peer_gatherer(out, n_voxels, group, mapping):
+    """The cached :class:`PeerGather` for outputs of these shapes (building one is a collective: symmetric
+    allocation + rendezvous; every rank arrives here with the same shapes in the same call)."""
+    spec = {k: (tuple(v.shape[1:]), v.dtype) for k, v in out.items()}
+    dev = next(iter(out.values())).device
+    key = (tuple((k, s, str(d)) for k, (s, d) in spec.items()), n_voxels, str(dev), id(group), mapping)
+    pg = _peer_gatherers.get(key)
+    if pg is None:
+        if len(_peer_gatherers) >= 4:       # each one holds full-size result tensors
+            _peer_gatherers.clear()
+        pg = _peer_gatherers[key] = PeerGather(spec, n_voxels, dev, group, mapping=mapping)
+    return pg
+
+
+def bd_sharded(y_full_or_local, n_voxels, solve, gather=True, group=None, peer_mapping="symm"):
     """Run ``solve(y_local) -> dict of [v_local, ...] tensors`` on this rank's rows.
 
     ``y_full_or_local`` is either the full ``[V, T]`` matrix (every rank slices its rows) or this
-    rank's slab already.  With ``gather`` the outputs are all-gathered to ``[V, ...]`` everywhere.
+    rank's slab already.  With ``gather`` the outputs are all-gathered to ``[V, ...]`` everywhere:
+    ``True`` over the process group's backend (NCCL / gloo, :func:`gather_rows`), ``"peer"`` by copy-engine
+    peer writes (:class:`PeerGather`, CUDA tensors on one node).  The peer path returns tensors OWNED by the
+    cached gatherer: they are overwritten by the next call with the same shapes -- clone what must survive it.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -218,4 +238,8 @@ def bd_sharded(y_full_or_local, n_voxels, solve, gather=True, group=None):
     out = solve(y_local)
     if not gather or world == 1:
         return out
+    if gather == "peer":
+        pg = _peer_gatherer(out, n_voxels, group, peer_mapping)
+        pg.fence()          # every rank is done with the previous result before anyone overwrites it
+        return dict(pg.gather(out))
     return {k: gather_rows(v, n_voxels, group) for k, v in out.items()}
