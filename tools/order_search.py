@@ -39,8 +39,19 @@ def main():
         f.write('#include "%s"\nnamespace pb { int inst(const %s<float> &a, cudaStream_t s) { return %s(a, s); } }\n'
                 % (header, args, launch))
     cands = []
-    for cj, crb, kj, kr, krb in itertools.product((0, 1), (0, 5, 7, 8, 10), (0, 1), (0, 1), (0, 5, 7, 8)):
-        cands.append({"CONV_JDESC": cj, "CONV_RB": crb, "CORR_JDESC": kj, "CORR_RDESC": kr, "CORR_RB": krb})
+    conv = [{"CONV_JDESC": cj, "CONV_RB": crb} for cj, crb in itertools.product((0, 1), (0, 5, 7, 8, 10))]
+    corr = [{"CORR_JDESC": kj, "CORR_RDESC": kr, "CORR_RB": krb}
+            for kj, kr, krb in itertools.product((0, 1), (0, 1), (0, 5, 7, 8))]
+    if os.environ.get("PB_SEARCH_DS"):      # data-stationary orders (all taps of one window position)
+        conv_ds = [{"CONV_DS": ds, "CONV_JDESC": cj} for ds, cj in itertools.product((1, 2), (0, 1))]
+        corr_ds = [{"CORR_DS": ds, "CORR_JDESC": kj} for ds, kj in itertools.product((1, 2), (0, 1))]
+        pairs = [(a, b) for a in conv_ds for b in corr + corr_ds] + [(a, b) for a in conv for b in corr_ds]
+    else:
+        pairs = [(a, b) for a in conv for b in corr]
+    for a, b in pairs:
+        c = dict(a)
+        c.update(b)
+        cands.append(c)
 
     def run(i):
         c = cands[i]
