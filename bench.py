@@ -25,6 +25,7 @@ The line printed by rank 0 follows the driver's contract; extra objects:
 from __future__ import annotations
 
 import argparse
+import gc
 import importlib.util
 import json
 import os
@@ -361,8 +362,12 @@ def main():
         nothing); the last gather is exposed.  Returns (ms per step, solver ms, gather ms), MAX over ranks."""
         main = torch.cuda.current_stream()
         overlap = side is not None and nbuf > 1
+        gc.collect()
+        gc.disable()     # a generation-2 pass of the collector is a 10-40 ms host pause (as timeit does)
+        out = None
         for _ in range(warmup):
-            gather(launch(0), 0)
+            out = launch(0)      # held until the next call returns, like in the timed loop: a launch that
+            gather(out, 0)       # allocates its outputs then finds the allocator in its steady state
             flush.fill_(1.0)
         barrier()
         marks, gmarks = [], []
@@ -398,6 +403,7 @@ def main():
             main.wait_stream(side)
         t1.record()
         barrier()
+        gc.enable()
         total = t0.elapsed_time(t1)
         flush_ms = sum(m[2].elapsed_time(m[3]) for m in marks)
         kern = [m[0].elapsed_time(m[1]) for m in marks]
@@ -509,6 +515,8 @@ def main():
         def step_e2e():
             return pb.bd(y_host, w["t_r"], lbda=w["lbda"], theta_0=w["theta_0"], hrf_dur=w["hrf_dur"],
                          bounds=[w["bounds"]], nb_iter=n)
+        gc.collect()
+        gc.disable()
         for _ in range(3):   # untimed calls: the pinned result blocks of consecutive calls (the caller still
             res = step_e2e()  # holds the previous result) are then cached; the third call was still 60 ms slow
         barrier()
@@ -520,6 +528,7 @@ def main():
             e2e_samples.append((time.perf_counter() - t_s) * 1e3)
         barrier()
         (e2e_s,) = max_over_ranks([(time.perf_counter() - t0) / args.steps])
+        gc.enable()
         d2h = sum(int(a.numel()) * a.element_size() for a in res[:4]) + \
             sum(int(res[4][k].numel()) * res[4][k].element_size() for k in ("J", "r", "g", "theta", "n_trace"))
         e2e = {"value": V_total / e2e_s, "unit": "voxels/s",
@@ -611,7 +620,7 @@ def main():
                 k_evs.append((ev(), ev()))
                 return deconv_batch(y2, h2, lb2, L2t, None, False, 1.0e-6, 6, c2["nb_iter"], events=k_evs[-1])
 
-            s_ms, _, _, _ = timed_steps(launch2, lambda out, b: None, 5, 3)
+            s_ms, _, _, each2 = timed_steps(launch2, lambda out, b: None, 5, 3)
             # the launch is so short that events around the Python call would time the host: these two sit
             # immediately around the C-ABI launch (the momentum-table kernel is part of the launch)
             k_ms = sum(a.elapsed_time(b) for a, b in k_evs[-5:]) / 5
@@ -620,6 +629,7 @@ def main():
                 "workload": workload_name("deconv", c2["voxels"], c2["n_scans"]), "dtype": "f32",
                 "value": c2["voxels"] / (s_ms * 1e-3), "unit": "voxels/s", "ms_per_step": s_ms, "steps": 5,
                 "warmup": 3, "nb_iter": c2["nb_iter"], "lbda": c2["lbda"],
+                "ms_each_call": [round(v, 3) for v in each2],   # events around each Python call (rank 0)
                 "note": "ms_per_step is the Python-level call (output allocation, host launch latency); the roofline "
                         "uses events placed around the kernel launch; 10 000 voxels are %.1f waves of the "
                         "grid: tail-bound" % (c2["voxels"] / max(1, sms * 24)),
@@ -641,13 +651,14 @@ def main():
             def path(b):
                 return deconv_lbda_path(y5, c5["t_r"], h5, lbdas, nb_iter=c5["nb_iter"], x0=x05)
 
-            s_ms, k_ms, _, _ = timed_steps(path, lambda out, b: None, 2, 1)
+            s_ms, k_ms, _, each5 = timed_steps(path, lambda out, b: None, 2, 2)
             launches += 2
             extra["cfg5_lbda_path_64_x_20k_x_600"] = {
                 "workload": "deconv_path_%d_lbda_x_%dk_voxels_x_%d_TRs" % (c5["n_lbda"], c5["voxels"] // 1000,
                                                                          c5["n_scans"]),
                 "dtype": "f32", "value": problems / (s_ms * 1e-3), "unit": "(lambda, voxel) problems/s",
-                "ms_per_step": s_ms, "steps": 2, "warmup": 1, "nb_iter": c5["nb_iter"],
+                "ms_per_step": s_ms, "steps": 2, "warmup": 2, "nb_iter": c5["nb_iter"],
+                "ms_each_call": [round(v, 3) for v in each5],
                 "note": "timed through deconv_lbda_path (public API): power iteration, launches, output "
                         "allocation and the J normalisation are inside ms_per_step",
                 "roofline": fp32_roofline("deconv", problems, c5["n_scans"], K5, c5["nb_iter"], k_ms,

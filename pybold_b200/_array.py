@@ -37,7 +37,24 @@ def to_device(x, dtype, device=None):
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=dtype).contiguous()
     arr = np.ascontiguousarray(np.asarray(x))
-    return torch.from_numpy(arr).to(device=device, dtype=dtype).contiguous()
+    return upload(arr, dtype, device)
+
+
+_PINNED_UPLOAD_LIMIT = 16 << 20
+
+
+def upload(arr, dtype, device):
+    """NumPy array -> device tensor of ``dtype``.  Small and medium arrays go through a pinned block (PyTorch
+    caches them) and an asynchronous copy: a pageable upload makes the host wait on the launch stream, and
+    that wait was measured to stall for tens of milliseconds now and then with the device idle
+    (tools/debug_e2e.py).  Larger arrays take the driver's own staged path."""
+    device = torch.device(device)
+    src = torch.from_numpy(arr)
+    if device.type != "cuda" or arr.nbytes > _PINNED_UPLOAD_LIMIT or arr.size == 0:
+        return src.to(device=device, dtype=dtype).contiguous()
+    stage = torch.empty(src.shape, dtype=dtype, pin_memory=True)
+    stage.copy_(src)                                   # converts on the host
+    return stage.to(device=device, non_blocking=True)
 
 
 _scalar_cache = {}
@@ -68,15 +85,7 @@ def per_voxel(value, V, dtype, device, name):
         arr = np.asarray(value, dtype=np.float64).reshape(-1)
         if arr.size == 1:
             return _device_scalar(float(arr[0]), dtype, torch.device(device)), 0
-        # through a pinned block (PyTorch caches them) and an asynchronous copy: a pageable upload makes the
-        # host wait on the launch stream, and that wait was measured to stall for tens of milliseconds now and
-        # then (tools/debug_e2e.py) -- with the device idle, since the solver launch follows it
-        stage = torch.empty(arr.size, dtype=dtype, pin_memory=True) if torch.device(device).type == "cuda" else None
-        if stage is None:
-            t = torch.as_tensor(arr).to(device=device, dtype=dtype)
-        else:
-            stage.copy_(torch.from_numpy(arr))
-            t = stage.to(device=device, non_blocking=True)
+        t = upload(arr, dtype, device)
     if t.numel() == 1:
         return t, 0
     if t.numel() != V:

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._array import like_input, per_voxel, pick_dtype, ptr, stream_ptr, to_device
+from ._array import like_input, per_voxel, pick_dtype, ptr, stream_ptr, to_device, upload
 from .hrf_model import MAX_DELTA, MIN_DELTA, hrf_len
 from .linear import ConvAndLinear, DiscretInteg
 from .utils import spectral_radius_est
@@ -145,7 +145,7 @@ def deconv_lbda_path(y, t_r, hrf, lbdas, nb_iter=200, x0=None, dtype=None, max_p
     V, T = yb.shape
     hd = to_device(hrf, dtype).reshape(-1).contiguous()
     K = hd.numel()
-    lb = torch.as_tensor(np.asarray(lbdas, dtype=np.float64).reshape(-1)).to(device=yb.device, dtype=dtype)
+    lb = upload(np.asarray(lbdas, dtype=np.float64).reshape(-1), dtype, yb.device)
     n_l = lb.numel()
     if x0 is None:
         x0 = np.random.randn(T)
