@@ -43,3 +43,21 @@ for Kx in (4, 8, 12, 20, 28):
     ms = timed(lambda: simple_convolve(kx, x))
     print("%-32s %8.3f ms  %7.1f GB/s  %.2f of measured HBM copy  (%.1f Tflop/s of FFMA)"
           % ("conv op (K=%d)" % Kx, ms, byt / ms / 1e6, byt / ms / 1e6 / peak, 2.0 * V * T * Kx / ms / 1e9))
+
+# the cfg3 shape (T = 300, K = 20), same bytes
+del x, xt
+V, T, K = 920000, 300, 20
+x = torch.randn((V, T), device="cuda")
+k = torch.rand(K, device="cuda")
+H = pb.ConvAndLinear(D, k, dim_in=T)
+xt = x.t().contiguous()
+byt = 2 * V * T * 4
+print("-- %d voxels x %d scans, K = %d --" % (V, T, K))
+for name, fn in [("integ op (cumsum)", lambda: D.op(x)), ("integ adj", lambda: D.adj(x)),
+                 ("conv op (K=20)", lambda: simple_convolve(k, x)), ("conv adj (K=20)", lambda: simple_retro_convolve(k, x)),
+                 ("hrfinteg op", lambda: H.op(x)), ("hrfinteg adj", lambda: H.adj(x)),
+                 ("layout adapter [T,V]->[V,T]", lambda: voxels_from_timeseries(xt)),
+                 ("torch transposed copy", lambda: xt.t().contiguous()),
+                 ("torch copy (reference)", lambda: x.clone())]:
+    ms = timed(fn)
+    print("%-32s %8.3f ms  %7.1f GB/s  %.2f of measured HBM copy (%.0f GB/s)" % (name, ms, byt / ms / 1e6, byt / ms / 1e6 / peak, peak))
