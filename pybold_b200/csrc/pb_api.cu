@@ -390,6 +390,9 @@ int run_deconv(pb::DeconvArgs<real> a, pb_stream_t stream) {
     const bool es = a.early_stopping && a.wind >= 2;
     pb::GenLayout lay = pb::GenLayout::make(a.T, a.K, es ? a.wind - 1 : 0, false);
     const size_t beta_bytes = ((size_t)a.nb_iter * sizeof(real) + 15) & ~(size_t)15;
+    // long series in double with the early-stopping ring: rows that do not fit move to the output rows
+    while (beta_bytes + lay.warp_bytes(sizeof(real)) > (size_t)d.max_smem_optin && lay.spill_ring_row()) {
+    }
     LaunchPlan p = plan_launch(d, beta_bytes, lay.warp_bytes(sizeof(real)), a.V, 8);
     if (!p.warps) return PB_ERR_UNSUPPORTED;
     auto kern = pb::generic_deconv_kernel<real>;

@@ -157,6 +157,8 @@ struct GenLayout {
     int tp;           // padded T (multiple of 4)
     int kp;           // padded K (multiple of 4)
     int ring_rows;    // wind - 1 for deconv with early stopping, else 0
+    int ring_smem;    // how many of them live in shared memory; up to three of the rest use the voxel's own
+                      // output rows (out_x, out_z, out_dz: free until the final store) as scratch
     size_t doubles;   // per-warp scratch doubles
     size_t reals;     // per-warp reals
     __host__ __device__ static GenLayout make(int T, int K, int ring_rows, bool with_theta) {
@@ -164,9 +166,17 @@ struct GenLayout {
         l.tp = (T + 3) & ~3;
         l.kp = (K + 3) & ~3;
         l.ring_rows = ring_rows;
+        l.ring_smem = ring_rows;
         l.doubles = with_theta ? (size_t)pb_scratch_doubles(l.kp) : (size_t)(3 * l.kp);
         l.reals = (size_t)4 * l.tp + l.kp + (size_t)ring_rows * l.tp;
         return l;
+    }
+    // move one more ring row out of shared memory; false when no output row is left to take it
+    __host__ bool spill_ring_row() {
+        if (ring_smem == 0 || ring_rows - ring_smem >= 3) return false;
+        --ring_smem;
+        reals -= (size_t)tp;
+        return true;
     }
     __host__ __device__ size_t warp_bytes(size_t real_size) const {
         return doubles * sizeof(double) + ((reals * real_size + 7) & ~(size_t)7);
@@ -253,6 +263,13 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
         const double lam = p.lam_of(v);
         const real step = (real)(1.0 / Lc), th = (real)(lam / Lc);
         real *Jv = p.out_J + v * (int64_t)p.nb_iter;
+        // ring row r: shared memory, or (long series in double) this voxel's output rows until the final store;
+        // a lane only ever reads back the elements it wrote itself
+        auto ring_row = [&](int r) -> real * {
+            if (r < lay.ring_smem) return g.ring + (size_t)r * lay.tp;
+            const int o = r - lay.ring_smem;
+            return (o == 0 ? p.out_x : (o == 1 ? p.out_z : p.out_dz)) + v * T;
+        };
         int n_done = 0;
         for (int k = 0; k < p.nb_iter; ++k) {
             g.forward();
@@ -262,7 +279,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
             }
             g.adjoint();
             double d0, d1;
-            real *uslot = es ? g.ring + (size_t)(k % nring) * lay.tp : nullptr;
+            real *uslot = es ? ring_row(k % nring) : nullptr;
             g.update(step, th, beta[k], uslot, false, d0, d1);
             n_done = k + 1;
             if (es && k > p.wind) {
@@ -273,7 +290,7 @@ __global__ void generic_deconv_kernel(DeconvArgs<real> p, GenLayout lay) {
                     real so = 0, sn = 0;
                     for (int m = 0; m < p.wind - 1; ++m) {
                         const int j = k - p.wind + 2 + m;
-                        const real u = g.ring[(size_t)(j % nring) * lay.tp + i];
+                        const real u = ring_row(j % nring)[i];
                         if (m < p.wind - sub) so += u; else sn += u;
                     }
                     sn += g.ws[i];

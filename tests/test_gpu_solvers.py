@@ -109,6 +109,30 @@ def test_deconv_early_stopping_group_kernel_with_work_queue(dt):
             assert rel(J[v, :n_o], np.asarray(Jo)) < 1e-9
 
 
+@pytest.mark.parametrize("T", [3300, 4096])
+def test_deconv_early_stopping_long_series_fp64(T):
+    """FP64 deconv with the reference's default early stopping on series beyond ~3200 scans: the generic
+    kernel's ring of past iterates no longer fits in shared memory next to its work rows, the oldest rows
+    then live in the voxel's own output rows until the final store.  Iteration count and results as the
+    oracle's."""
+    import pybold_b200 as pb
+    y = gen_voxels(2, T, 1.0, 20.0, seed0=8800 + T)
+    h, _ = orc.spm_hrf(1.0, 1.0, 20.0, True)
+    x0 = np.random.RandomState(3).randn(T)
+    kw = dict(lbda=1.0, early_stopping=True, tol=5e-2, wind=6, nb_iter=60)
+    x, z, dz, J, _, _ = pb.deconv(y, 1.0, h, x0=x0, **kw)
+    n_it = np.sum(~np.isnan(J), axis=1)
+    Lc = 0.9 * orc.spectral_radius_est(orc.HrfIntegOperator(h, T), x0)
+    for v in range(2):
+        xo, zo, wo, Jo, n_o = orc.deconv_fixed_lbda(y[v], h, 1.0, lipschitz=Lc, early_stopping=True, tol=5e-2,
+                                                    wind=6, nb_iter=60)
+        assert n_it[v] == n_o and 7 < n_o < 60
+        assert rel(z[v], zo) < 1e-9 and rel(x[v], xo) < 1e-9 and rel(J[v, :n_o], Jo) < 1e-9
+    # without early stopping the same shapes run as before
+    x2, z2, dz2, J2, _, _ = pb.deconv(y, 1.0, h, x0=x0, lbda=1.0, early_stopping=False, nb_iter=12)
+    assert J2.shape[1] == 12 and np.all(np.isfinite(z2))
+
+
 def test_deconv_ragged_and_edge_shapes():
     import pybold_b200 as pb
     rng = np.random.RandomState(3)

@@ -41,6 +41,28 @@ for t_r in (1.0, 0.72, 0.5, 0.32):
             bad += bool(flag)
             rows.append((max(ez, eh, et), vid, T, K))
             print("variant %9d  T %4d  K %2d  z %.1e  h %.1e  theta %.1e%s" % (vid, T, K, ez, eh, et, flag), flush=True)
+# deconv (fixed lambda, with and without early stopping) over a comb of series lengths: FP32 against FP64
+drows = []
+for t_r in (1.0, 0.72, 0.5, 0.32):
+    K = hrf_len(t_r, 20.0)
+    h = pb.spm_hrf(1.0, t_r, 20.0)[0]
+    for T in list(range(K + 4, 4097, 97)) + [4096]:
+        y = gen_voxels(3, T, t_r, 20.0, seed0=9500 + T)
+        x0 = np.random.RandomState(T).randn(T)
+        for es in (False, True):
+            a = pb.deconv(y, t_r, h, lbda=0.8, nb_iter=25, early_stopping=es, tol=1e-3, x0=x0)
+            b = pb.deconv(y.astype(np.float32), t_r, h.astype(np.float32), lbda=0.8, nb_iter=25, early_stopping=es,
+                          tol=1e-3, x0=x0.astype(np.float32))
+            e = rel(b[1], a[1])
+            same_len = np.asarray(a[3]).shape == np.asarray(b[3]).shape
+            tol = 2e-4
+            flag = "" if (e < tol and same_len) else "  <-- z %.1e, trace shapes %s / %s" % (e, np.asarray(a[3]).shape, np.asarray(b[3]).shape)
+            bad += bool(flag)
+            drows.append((e, T, K, es))
+            if flag:
+                print("deconv T %4d K %2d early_stopping %s%s" % (T, K, es, flag), flush=True)
+drows.sort(reverse=True)
+print("deconv: %d cases, worst z errors %s" % (len(drows), [(T, K, es, "%.1e" % e) for e, T, K, es in drows[:5]]))
 rows.sort(reverse=True)
 print("worst:", [(v, T, K, "%.1e" % e) for e, v, T, K in rows[:6]])
 print("%d (variant, T) cases, %d above their bound" % (len(rows), bad))
