@@ -91,6 +91,15 @@ def deconv_batch(y, hrf, lbda, lipschitz, w0=None, early_stopping=True, tol=1.0e
     return x, z, dz, J, n_iter
 
 
+def _lipschitz_cst(est, dtype):
+    """``0.9 * spectral_radius_est`` (bold_signal.py:52), the product taken in double like the reference does
+    and rounded once to the build's type: the same constant on every path that solves the same problem."""
+    if isinstance(est, torch.Tensor):
+        return (0.9 * est.double()).to(dtype)
+    est = np.asarray(est, dtype=np.float64)
+    return 0.9 * float(est) if est.ndim == 0 else 0.9 * est       # scalars stay host floats (cached on the device)
+
+
 def deconv(y, t_r, hrf, lbda=None, early_stopping=True, tol=1.0e-6,  # noqa
            wind=6, nb_iter=1000, nb_sub_iter=1000, verbose=0, x0=None, sigma=None, dtype=None):
     """Sparse deconvolution with a known HRF (pybold/bold_signal.py:13-214).
@@ -111,7 +120,7 @@ def deconv(y, t_r, hrf, lbda=None, early_stopping=True, tol=1.0e-6,  # noqa
     if x0 is None:
         x0 = np.random.randn(T)
     est = spectral_radius_est(H, (T,), x0=to_device(x0, dtype))
-    lipschitz = 0.9 * (est if isinstance(est, torch.Tensor) else torch.as_tensor(est, dtype=dtype))
+    lipschitz = _lipschitz_cst(est, dtype)
 
     if lbda is None:
         from .noise import deconv_auto_lbda
@@ -150,7 +159,7 @@ def deconv_lbda_path(y, t_r, hrf, lbdas, nb_iter=200, x0=None, dtype=None, max_p
     if x0 is None:
         x0 = np.random.randn(T)
     est = spectral_radius_est(ConvAndLinear(DiscretInteg(), hd, dim_in=T), (T,), x0=to_device(x0, dtype))
-    lipschitz = torch.full((1,), 0.9 * float(est), dtype=dtype, device=yb.device)   # bold_signal.py:52
+    lipschitz = per_voxel(_lipschitz_cst(est, dtype), 1, dtype, yb.device, "lipschitz")[0]
     outs = [torch.empty((n_l, V, T), dtype=dtype, device=yb.device) for _ in range(3)]
     J = torch.empty((n_l, V, nb_iter), dtype=dtype, device=yb.device)
     n_iter = torch.empty(n_l * V, dtype=torch.int32, device=yb.device)

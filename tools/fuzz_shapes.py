@@ -63,6 +63,42 @@ for t_r in (1.0, 0.72, 0.5, 0.32):
                 print("deconv T %4d K %2d early_stopping %s%s" % (T, K, es, flag), flush=True)
 drows.sort(reverse=True)
 print("deconv: %d cases, worst z errors %s" % (len(drows), [(T, K, es, "%.1e" % e) for e, T, K, es in drows[:5]]))
+# the other entry points on a coarser comb: no exception, finite results, FP32 close to FP64
+other = 0
+for t_r in (1.0, 0.5):
+    K = hrf_len(t_r, 20.0)
+    h = pb.spm_hrf(1.0, t_r, 20.0)[0]
+    for T in list(range(K + 4, 4097, 389)) + [4096]:
+        y = gen_voxels(2, T, t_r, 20.0, seed0=9700 + T)
+        tolT = 2e-4 if T <= 1300 else 3e-3
+        try:
+            a = pb.bd(y, t_r, lbda=1.2, theta_0=2.0, nb_iter=6, early_stopping=True, tol=1e-3)
+            b = pb.bd(y.astype(np.float32), t_r, lbda=1.2, theta_0=2.0, nb_iter=6, early_stopping=True, tol=1e-3)
+            ok = np.all(np.isfinite(a[1])) and np.all(np.isfinite(b[1]))
+            same = len(np.atleast_2d(a[4]["J"])[0]) == len(np.atleast_2d(b[4]["J"])[0])
+            e = rel(b[1], a[1]) if same else 0.0       # FP32 may stop one outer iteration apart
+            msg = "" if (ok and e < tolT) else "  <-- bd early stopping: finite %s, z %.1e" % (ok, e)
+            aa = pb.deconv(y, t_r, h, lbda=None, sigma=0.3, nb_iter=3, nb_sub_iter=8)
+            bb = pb.deconv(y.astype(np.float32), t_r, h.astype(np.float32), lbda=None, sigma=0.3, nb_iter=3, nb_sub_iter=8)
+            e2 = rel(bb[1], aa[1])
+            msg += "" if (np.all(np.isfinite(aa[1])) and e2 < 1e-3) else "  <-- deconv(lbda=None): z %.1e" % e2
+            z = a[1]
+            he, _ = pb.hrf_estim(z, y, t_r, 20.0)
+            he32, _ = pb.hrf_estim(z.astype(np.float32), y.astype(np.float32), t_r, 20.0)
+            e3 = rel(he32, he)
+            msg += "" if (np.all(np.isfinite(he)) and e3 < tolT * 5) else "  <-- hrf_estim: h %.1e" % e3
+            lp = pb.bold_signal.deconv_lbda_path(y.astype(np.float32), t_r, h.astype(np.float32), [0.3, 0.9], nb_iter=6,
+                                                 x0=np.ones(T, dtype=np.float32))
+            one = pb.deconv(y.astype(np.float32), t_r, h.astype(np.float32), lbda=0.9, nb_iter=6, early_stopping=False,
+                            x0=np.ones(T, dtype=np.float32))
+            msg += "" if np.array_equal(lp[1][1], one[1]) else "  <-- lambda path != single-lambda call"
+        except Exception as exc:               # noqa: BLE001
+            msg = "  <-- EXCEPTION %s" % str(exc)[:100]
+        other += 1
+        bad += bool(msg)
+        if msg:
+            print("other entry points T %4d K %2d%s" % (T, K, msg), flush=True)
+print("other entry points (bd with early stopping, deconv(lbda=None), hrf_estim, lambda path): %d shapes" % other)
 rows.sort(reverse=True)
 print("worst:", [(v, T, K, "%.1e" % e) for e, v, T, K in rows[:6]])
 print("%d (variant, T) cases, %d above their bound" % (len(rows), bad))
