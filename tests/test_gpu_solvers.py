@@ -422,6 +422,19 @@ def test_bd_streamed_host_batch_equals_single_launch():
         assert np.array_equal(u, v.cpu().numpy())
     for k in ("J", "r", "g", "theta", "n_trace"):
         assert np.array_equal(a[4][k], b[4][k].cpu().numpy()), k
+    # results too large for pinned host tensors go through the two pinned staging slots into pageable
+    # memory: same bits (forced here by a zero limit); a pinned input tensor is uploaded in place
+    old_lim = bs._PINNED_RESULT_LIMIT
+    bs._STREAM_TARGET_CHUNK, bs._PINNED_RESULT_LIMIT = 4096, 0
+    try:
+        c = pb.bd(torch.from_numpy(y.astype(np.float32)).pin_memory(), 1.0, lbda=lb, z_0=z0, nb_iter=6)
+    finally:
+        bs._STREAM_TARGET_CHUNK, bs._PINNED_RESULT_LIMIT = old, old_lim
+    assert isinstance(c[0], torch.Tensor) and not c[0].is_cuda and not c[0].is_pinned()
+    for u, v in zip(a[:4], c[:4]):
+        assert np.array_equal(u, v.numpy())
+    for k in ("J", "r", "g", "theta", "n_trace"):
+        assert np.array_equal(a[4][k], c[4][k].numpy()), k
 
 
 def test_deconv_auto_lambda_vs_oracle():
