@@ -29,17 +29,21 @@ VARIANTS = [
 
 # Group variants (pb_fastg.cuh): (real, R, KMAX, G lanes per voxel, TAIL, warps per CTA, min CTAs/SM).
 # Used by bd when early stopping is off; 32/G voxels per warp.  Picked by tools/exp_bdg.cu.
+# Round 2, end: the two-voxels-per-warp variants run as ONE-warp CTAs, twelve per SM (same 12 warps and 168
+# registers as four-warp CTAs x 3, no CTA-wide barrier, one task queue reader per CTA): measured +1.6 % at
+# T = 300, +3.5 % at 240 / K = 27, +7.7 % at 200, +7.4 % at 320 (tools/exp_bdg.cu sets 9, 10); the four-voxel
+# variants (G = 8) measured the same either way and keep four-warp CTAs.
 GVARIANTS = [
-    ("float", 19, 20, 16, 8, 4, 3),    # T in [296, 304], K <= 20   (cfg3: T = 300)
-    ("float", 15, 28, 16, 8, 4, 3),    # T in [232, 240], K <= 28   (ICASSP native: T = 240, K = 27)
+    ("float", 19, 20, 16, 8, 1, 12),   # T in [296, 304], K <= 20   (cfg3: T = 300)
+    ("float", 15, 28, 16, 8, 1, 12),   # T in [232, 240], K <= 28   (ICASSP native: T = 240, K = 27)
     ("double", 19, 20, 16, 8, 4, 1),   # parity build of the group kernel
 ] + [
     # general coverage of 192 < T <= 320 (two voxels per warp), any tail (TAIL = R)
-    ("float", R, K, 16, R, 4, 3) for K in (20, 28) for R in range(13, 21)
+    ("float", R, K, 16, R, 1, 12) for K in (20, 28) for R in range(13, 21)
 ] + [
     # 320 < T <= 352 with K <= 20 (measured +8 % over the one-warp CTA variant; with 28 taps the
     # register pressure makes it a tie, not built)
-    ("float", R, 20, 16, R, 4, 3) for R in (21, 22)
+    ("float", R, 20, 16, R, 1, 12) for R in (21, 22)
 ] + [
     # short series, 40 < T <= 192: four voxels per warp (G = 8), every slot maskable.  Launch bounds: the
     # 28-tap variants spill at 168 registers (measured +8 % at R = 16, +23 % at R = 24 with 255, round 2)

@@ -118,6 +118,39 @@ int main(int argc, char **argv) {
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3", b, 100, true);
         b.free_all();
+    } else if (set == 9) {      // round 2: CTA shapes under the work queue -- 13 one-warp CTAs (152 registers), 6 x 2, 12 x 1
+        Bufs b; b.alloc(42624, 300, 1.0, 100);
+        rung<19, 20, 16, 8, 4, 3>("G16 R19 W4 M3 (default)", b, 100, true);
+        rung<19, 20, 16, 8, 1, 13>("G16 R19 W1 M13 (13 warps)", b, 100);
+        rung<19, 20, 16, 8, 1, 12>("G16 R19 W1 M12", b, 100);
+        rung<19, 20, 16, 8, 2, 6>("G16 R19 W2 M6", b, 100);
+        rung<19, 20, 16, 8, 1, 14>("G16 R19 W1 M14 (14 warps)", b, 100);
+        b.free_all();
+    } else if (set == 10) {     // round 2: one-warp CTAs (W1 M12) against W4 M3 on other group variants
+        {
+            Bufs b; b.alloc(21312, 240, 0.75, 100);
+            rung<15, 28, 16, 8, 4, 3>("G16 R15 K28 W4 M3 (T=240)", b, 100, true);
+            rung<15, 28, 16, 8, 1, 12>("G16 R15 K28 W1 M12 (T=240)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(21312, 200, 1.0, 100);
+            rung<13, 20, 16, 13, 4, 3>("G16 R13 K20 W4 M3 (T=200)", b, 100, true);
+            rung<13, 20, 16, 13, 1, 12>("G16 R13 K20 W1 M12 (T=200)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(21312, 320, 1.0, 100);
+            rung<20, 20, 16, 20, 4, 3>("G16 R20 K20 W4 M3 (T=320)", b, 100, true);
+            rung<20, 20, 16, 20, 1, 12>("G16 R20 K20 W1 M12 (T=320)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 128, 1.0, 100);
+            rung<16, 20, 8, 16, 4, 3>("G8 R16 K20 W4 M3 (T=128)", b, 100, true);
+            rung<16, 20, 8, 16, 1, 12>("G8 R16 K20 W1 M12 (T=128)", b, 100);
+            b.free_all();
+        }
     } else if (set == 4) {      // round 2: blocked shared-memory halo exchange, occupancy
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3 (r01)", b, 100, true);
