@@ -11,7 +11,7 @@ VARIANTS = [
     # in tools/exp_bd.cu on a B200 (profiles/r01_launch_bounds_sweep.txt)
     ("float", 10, 20, True, 4, 5),    # cfg2 / cfg3: T = 300, K = 20
     ("float", 40, 28, True, 8, 1),    # cfg4: T = 1200, K = 28
-    ("float", 20, 20, True, 4, 3),    # cfg5: T = 600, K = 20
+    ("float", 20, 20, True, 1, 12),   # cfg5: T = 600, K = 20
     ("float", 8, 28, False, 4, 4),    # ICASSP native: T = 240, K = 27
     ("float", 10, 20, False, 4, 5),
     ("float", 10, 32, False, 4, 3),
@@ -52,7 +52,7 @@ GVARIANTS = [
     # ... but with 28 taps the four double-precision scratch areas of a warp (8.5 KB per voxel) leave room for
     # one CTA per SM only: two voxels per warp with few samples per lane are faster (measured, round 2:
     # T = 96 +14 %, T = 128 +9 %, T = 190 +44 %; profiles/r02_exp_short_series.txt)
-    ("float", R, 28, 16, R, 4, 3) for R in (4, 6, 8, 10, 12)
+    ("float", R, 28, 16, R, 1, 12) for R in (4, 6, 8, 10, 12)
 ]
 
 
