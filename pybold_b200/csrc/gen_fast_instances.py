@@ -36,7 +36,7 @@ VARIANTS = [
 GVARIANTS = [
     ("float", 19, 20, 16, 8, 1, 12),   # T in [296, 304], K <= 20   (cfg3: T = 300)
     ("float", 15, 28, 16, 8, 1, 12),   # T in [232, 240], K <= 28   (ICASSP native: T = 240, K = 27)
-    ("double", 19, 20, 16, 8, 4, 1),   # parity build of the group kernel
+    ("double", 19, 20, 16, 8, 1, 8),   # parity build of the group kernel
 ] + [
     # general coverage of 192 < T <= 320 (two voxels per warp), any tail (TAIL = R)
     ("float", R, K, 16, R, 1, 12) for K in (20, 28) for R in range(13, 21)
