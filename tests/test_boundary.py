@@ -148,3 +148,29 @@ def test_db3_highpass_filter_has_its_defining_properties():
     for shift in (0, 2, 4):
         hi_s = np.concatenate([np.zeros(shift), g])[:len(g)]
         assert abs(np.sum(lo * hi_s)) < 1e-10
+
+
+def test_host_side_parameter_plumbing():
+    """Host logic that needs no GPU: the Lipschitz constant is 0.9 x the estimate with the product taken in double
+    (one expression for every deconv path), scalar parameters stay host floats until the launch, arrays are
+    checked against the batch size, NumPy uploads keep values and dtype (CPU device = the plain path)."""
+    import numpy as np
+    import torch
+    from pybold_b200._array import per_voxel, upload
+    from pybold_b200.bold_signal import _lipschitz_cst
+    est32 = float(np.float32(1234.5678))
+    c = _lipschitz_cst(est32, torch.float32)
+    assert isinstance(c, float) and c == 0.9 * est32
+    cb = _lipschitz_cst(np.array([1.0, 2.0]), torch.float64)
+    assert np.allclose(cb, [0.9, 1.8])
+    ct = _lipschitz_cst(torch.tensor([3.0], dtype=torch.float32), torch.float32)
+    assert ct.dtype == torch.float32 and float(ct[0]) == float(np.float32(0.9 * 3.0))
+    t = upload(np.arange(6, dtype=np.float64).reshape(2, 3), torch.float32, "cpu")
+    assert t.dtype == torch.float32 and t.shape == (2, 3) and t.is_contiguous() and float(t[1, 2]) == 5.0
+    v, stride = per_voxel(np.linspace(0.5, 1.5, 4), 4, torch.float64, "cpu", "lbda")
+    assert stride == 1 and v.shape == (4,) and float(v[3]) == 1.5
+    s, stride = per_voxel(1.7, 4, torch.float64, "cpu", "lbda")
+    assert stride == 0 and s.numel() == 1 and float(s[0]) == 1.7
+    assert per_voxel(1.7, 9, torch.float64, "cpu", "lbda")[0] is s        # cached: no upload per call
+    with pytest.raises(ValueError):
+        per_voxel(np.ones(3), 4, torch.float64, "cpu", "lbda")
