@@ -47,7 +47,8 @@ GVARIANTS = [
 ] + [
     # short series, 40 < T <= 192: four voxels per warp (G = 8), every slot maskable.  Launch bounds: the
     # 28-tap variants spill at 168 registers (measured +8 % at R = 16, +23 % at R = 24 with 255, round 2)
-    ("float", R, 20, 8, R, 4, 3) for R in (10, 13, 16, 20, 24)
+    # (one-warp CTAs where they measured faster: T = 64 +5.9 %, 100 +2.8 %, 150 +2.4 %; R = 16 the same, R = 24 -0.9 %)
+    ("float", R, 20, 8, R, 1 if R in (10, 13, 20) else 4, 12 if R in (10, 13, 20) else 3) for R in (10, 13, 16, 20, 24)
 ] + [
     # ... but with 28 taps the four double-precision scratch areas of a warp (8.5 KB per voxel) leave room for
     # one CTA per SM only: two voxels per warp with few samples per lane are faster (measured, round 2:

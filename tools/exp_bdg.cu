@@ -151,6 +151,31 @@ int main(int argc, char **argv) {
             rung<16, 20, 8, 16, 1, 12>("G8 R16 K20 W1 M12 (T=128)", b, 100);
             b.free_all();
         }
+    } else if (set == 11) {     // round 2: one-warp CTAs for the four-voxels-per-warp variants (G = 8, K <= 20)
+        {
+            Bufs b; b.alloc(28416, 64, 1.0, 100);
+            rung<10, 20, 8, 10, 4, 3>("G8 R10 W4 M3 (T=64)", b, 100, true);
+            rung<10, 20, 8, 10, 1, 12>("G8 R10 W1 M12 (T=64)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 100, 1.0, 100);
+            rung<13, 20, 8, 13, 4, 3>("G8 R13 W4 M3 (T=100)", b, 100, true);
+            rung<13, 20, 8, 13, 1, 12>("G8 R13 W1 M12 (T=100)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 150, 1.0, 100);
+            rung<20, 20, 8, 20, 4, 3>("G8 R20 W4 M3 (T=150)", b, 100, true);
+            rung<20, 20, 8, 20, 1, 12>("G8 R20 W1 M12 (T=150)", b, 100);
+            b.free_all();
+        }
+        {
+            Bufs b; b.alloc(28416, 190, 1.0, 100);
+            rung<24, 20, 8, 24, 4, 3>("G8 R24 W4 M3 (T=190)", b, 100, true);
+            rung<24, 20, 8, 24, 1, 12>("G8 R24 W1 M12 (T=190)", b, 100);
+            b.free_all();
+        }
     } else if (set == 4) {      // round 2: blocked shared-memory halo exchange, occupancy
         Bufs b; b.alloc(42624, 300, 1.0, 100);
         rung<19, 20, 16, 8, 4, 3>("G16 R19 K20 T8 W4 M3 (r01)", b, 100, true);
