@@ -32,7 +32,7 @@ VARIANTS = [
 # Round 2, end: the two-voxels-per-warp variants run as ONE-warp CTAs, twelve per SM (same 12 warps and 168
 # registers as four-warp CTAs x 3, no CTA-wide barrier, one task queue reader per CTA): measured +1.6 % at
 # T = 300, +3.5 % at 240 / K = 27, +7.7 % at 200, +7.4 % at 320 (tools/exp_bdg.cu sets 9, 10); the four-voxel
-# variants (G = 8) measured the same either way and keep four-warp CTAs.
+# variants (G = 8) gain 2 ... 6 % at R = 10, 13, 20 and nothing at R = 16, 24 (kept on four-warp CTAs).
 GVARIANTS = [
     ("float", 19, 20, 16, 8, 1, 12),   # T in [296, 304], K <= 20   (cfg3: T = 300)
     ("float", 15, 28, 16, 8, 1, 12),   # T in [232, 240], K <= 28   (ICASSP native: T = 240, K = 27)
